@@ -1,0 +1,130 @@
+"""ctypes binding of libdogs_b200.so (the C-ABI declared in include/dogs_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or fails
+to load, importing any operator of this package raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdogs_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class DgrParams(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("depth_threshold", C.c_float),
+        ("prefiltered", C.c_int32), ("antialiasing", C.c_int32), ("debug", C.c_int32),
+        ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+        ("campos", C.c_void_p),
+    ]
+
+
+class DgrForwardInfo(C.Structure):
+    _fields_ = [
+        ("num_rendered", C.c_int32), ("num_visible", C.c_int32),
+        ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t),
+        ("image_bytes", C.c_size_t), ("scratch_bytes", C.c_size_t),
+    ]
+
+
+class DgrLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "geom_record", "geom_clamped", "geom_tiles", "geom_bytes",
+        "bin_point_list", "bin_tile_keys", "bin_bytes",
+        "img_ranges", "img_final_T", "img_n_contrib", "img_bytes")]
+
+
+class AdmmTensors(C.Structure):
+    _fields_ = [("g", C.c_void_p * 6)]
+
+
+# name -> (argtypes); every entry point returns int except the two noted below.
+_P = C.c_void_p
+SIGNATURES = {
+    "dgr_forward": [C.POINTER(DgrParams)] + [_P] * 8 + [_P, _P, _P] + [ALLOC_FN, _P] * 4
+                   + [C.POINTER(DgrForwardInfo), _P],
+    "dgr_backward": [C.POINTER(DgrParams), C.c_int32] + [_P] * 8 + [_P] + [_P] * 3 + [_P, _P]
+                    + [_P] * 9 + [ALLOC_FN, _P, _P],
+    "dgr_visible_filter": [C.POINTER(DgrParams), _P, _P, _P, _P, _P, _P],
+    "dgr_mark_visible": [C.c_int32, _P, _P, _P, _P, _P],
+    "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
+    "dgr_sparse_adam": [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
+                        C.c_uint32, C.c_uint32, _P],
+    "fssim_forward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 6 + [_P],
+    "fssim_backward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 7 + [_P],
+    "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],
+    "admm_pack": [C.POINTER(AdmmTensors), _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P],
+    "admm_unpack_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, C.c_int64, _P, C.c_float, _P, _P],
+    "admm_penalty": [C.POINTER(AdmmTensors)] * 3 + [_P, C.c_int64, _P, _P, _P],
+    "dogs_last_error": [],
+    "dogs_abi_version": [],
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library on first use; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m dogs_b200.build` "
+                "(there is no CPU or PyTorch fallback for these operators)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib.dogs_last_error.restype = C.c_char_p
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().dogs_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a tensor; None / empty tensors map to NULL (the reference's convention:
+    missing optionals are empty tensors whose data_ptr is null, __init__.py:248-261)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Allocator:
+    """Allocation callback backed by torch's caching allocator (mirrors resizeFunctional,
+    rasterize_points.cu:30-36).  Keeps every buffer it hands out alive in `self.buffers`."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buffers = []
+        self.cb = ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+        self.buffers.append(t)
+        return t.data_ptr()
+
+    @property
+    def last(self):
+        return self.buffers[-1] if self.buffers else None
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (dogs_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32")
+    return t.contiguous()

@@ -1,0 +1,283 @@
+// C-ABI entry points of the rasterizer (include/dogs_b200.h).  Host orchestration only:
+// carves the caller-allocated buffers, launches the stage kernels on the caller's stream.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace dogs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what, bool debug, cudaStream_t s) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && debug) e = cudaStreamSynchronize(s);  // CHECK_CUDA, auxiliary.h:177-184
+  if (e != cudaSuccess) {
+    set_error("[CUDA ERROR] in %s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// ---- buffer layouts ---------------------------------------------------------------------
+size_t GeomState::bytes(size_t P) {
+  Carver c(nullptr);
+  c.take<SplatRecord>(P); c.take<uint8_t>(P); c.take<uint32_t>(P); c.take<uint32_t>(P);
+  c.take<uint32_t>(P); c.take<uint32_t>(P);
+  return c.off;
+}
+GeomState GeomState::carve(char* p, size_t P) {
+  Carver c(p);
+  GeomState g;
+  g.rec = c.take<SplatRecord>(P);
+  g.clamped = c.take<uint8_t>(P);
+  g.tiles = c.take<uint32_t>(P);
+  g.depth_key = c.take<uint32_t>(P);
+  g.sorted_idx = c.take<uint32_t>(P);
+  g.offsets = c.take<uint32_t>(P);
+  return g;
+}
+size_t BinState::bytes(size_t R) {
+  Carver c(nullptr);
+  c.take<uint32_t>(R); c.take<uint32_t>(R);
+  return c.off;
+}
+BinState BinState::carve(char* p, size_t R) {
+  Carver c(p);
+  BinState b;
+  b.point_list = c.take<uint32_t>(R);
+  b.tile_keys = c.take<uint32_t>(R);
+  return b;
+}
+size_t ImgState::bytes(size_t N, size_t T) {
+  Carver c(nullptr);
+  c.take<uint2>(T); c.take<float>(N); c.take<uint32_t>(N); c.take<float>(3 * N); c.take<float>(N);
+  return c.off;
+}
+ImgState ImgState::carve(char* p, size_t N, size_t T) {
+  Carver c(p);
+  ImgState im;
+  im.ranges = c.take<uint2>(T);
+  im.final_T = c.take<float>(N);
+  im.n_contrib = c.take<uint32_t>(N);
+  im.pix_color = c.take<float>(3 * N);
+  im.pix_invdepth = c.take<float>(N);
+  return im;
+}
+
+// getHigherMsb (rasterizer_impl.cu:35-50): number of bits needed for tile ids, 2^bit > T.
+static int higher_msb(uint32_t n) {
+  int bit = 0;
+  while (bit < 32 && (n >> bit)) bit++;
+  return bit;
+}
+
+static int validate(const DgrParams* prm) {
+  if (!prm) { set_error("DgrParams is null"); return 1; }
+  if (prm->P < 0 || prm->W <= 0 || prm->H <= 0) {
+    set_error("invalid sizes P=%d W=%d H=%d", prm->P, prm->W, prm->H);
+    return 1;
+  }
+  if (prm->D < 0 || prm->D > 3) { set_error("sh_degree %d out of range 0..3", prm->D); return 1; }
+  if (!prm->bg || !prm->viewmatrix || !prm->projmatrix || !prm->campos) {
+    set_error("bg/viewmatrix/projmatrix/campos must be device pointers");
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace dogs
+
+using namespace dogs;
+
+extern "C" {
+
+const char* dogs_last_error(void) { return g_err; }
+int dogs_abi_version(void) { return DOGS_B200_ABI_VERSION; }
+
+int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t R, DgrLayout* out) {
+  if (!out) return 1;
+  const size_t N = (size_t)W * H;
+  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  GeomState g = GeomState::carve(nullptr, P);
+  BinState b = BinState::carve(nullptr, R);
+  ImgState im = ImgState::carve(nullptr, N, T);
+  out->geom_record = (size_t)g.rec;
+  out->geom_clamped = (size_t)g.clamped;
+  out->geom_tiles = (size_t)g.tiles;
+  out->geom_bytes = GeomState::bytes(P);
+  out->bin_point_list = (size_t)b.point_list;
+  out->bin_tile_keys = (size_t)b.tile_keys;
+  out->bin_bytes = BinState::bytes(R);
+  out->img_ranges = (size_t)im.ranges;
+  out->img_final_T = (size_t)im.final_T;
+  out->img_n_contrib = (size_t)im.n_contrib;
+  out->img_bytes = ImgState::bytes(N, T);
+  return 0;
+}
+
+int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, const float* sh,
+                const float* colors_precomp, const float* opacities, const float* scales,
+                const float* rotations, const float* cov3D_precomp, float* out_color,
+                float* out_invdepth, int32_t* radii, dogs_alloc_fn geom_alloc, void* geom_user,
+                dogs_alloc_fn binning_alloc, void* binning_user, dogs_alloc_fn image_alloc,
+                void* image_user, dogs_alloc_fn scratch_alloc, void* scratch_user,
+                DgrForwardInfo* info, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (validate(prm)) return 1;
+  const DgrParams& p = *prm;
+  if (!means3D && p.P > 0) { set_error("means3D is null"); return 1; }
+  if ((colors_precomp == nullptr) == (dc == nullptr && sh == nullptr) && p.P > 0) {
+    set_error("Please provide excatly one of either SHs or precomputed colors!");
+    return 1;
+  }
+  if (colors_precomp == nullptr && p.P > 0 && (dc == nullptr || (p.D > 0 && (sh == nullptr || p.M < (p.D + 1) * (p.D + 1) - 1)))) {
+    set_error("SH input incomplete: need dc[P,1,3] and sh[P,M>=%d,3] for degree %d", (p.D + 1) * (p.D + 1) - 1, p.D);
+    return 1;
+  }
+  if (((scales == nullptr || rotations == nullptr) == (cov3D_precomp == nullptr)) && p.P > 0) {
+    set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    return 1;
+  }
+  if (!geom_alloc || !binning_alloc || !image_alloc || !scratch_alloc) {
+    set_error("allocation callbacks must not be null");
+    return 1;
+  }
+  const size_t P = p.P, N = (size_t)p.W * p.H;
+  const uint32_t gx = (p.W + TILE_X - 1) / TILE_X, gy = (p.H + TILE_Y - 1) / TILE_Y;
+  const size_t T = (size_t)gx * gy;
+  const bool dbg = p.debug != 0;
+
+  const size_t geom_bytes = GeomState::bytes(P), img_bytes = ImgState::bytes(N, T);
+  char* geom_p = geom_alloc(geom_user, geom_bytes);
+  char* img_p = image_alloc(image_user, img_bytes);
+  if (!geom_p || !img_p) { set_error("allocation callback returned null"); return 1; }
+  GeomState g = GeomState::carve(geom_p, P);
+  ImgState im = ImgState::carve(img_p, N, T);
+
+  uint32_t R = 0;
+  size_t scratch1_bytes = 0;
+  if (P > 0) {
+    if (launch_preprocess_fwd(p, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
+                              cov3D_precomp, radii, g, s)) return 1;
+    // depth order of the Gaussians (ties broken by index: the sort is stable)
+    scratch1_bytes = align_up(P * 4) * 2 + sort_pairs_scratch_bytes(P) + scan_scratch_bytes(P) + 256;
+    char* sc = scratch_alloc(scratch_user, scratch1_bytes);
+    if (!sc) { set_error("scratch allocation failed"); return 1; }
+    Carver cv(sc);
+    uint32_t* keys_b = cv.take<uint32_t>(P);
+    uint32_t* vals_b = cv.take<uint32_t>(P);
+    uint32_t* total = cv.take<uint32_t>(1);
+    char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(P));
+    char* scan_scratch = cv.take<char>(scan_scratch_bytes(P));
+    launch_iota(g.sorted_idx, P, s);
+    int in_b = 0;
+    // 4 passes of 8 bits => the result is back in (depth_key, sorted_idx)
+    if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b)) return 1;
+    if (in_b) cudaMemcpyAsync(g.sorted_idx, vals_b, P * 4, cudaMemcpyDeviceToDevice, s);
+    if (exclusive_scan_u32(g.tiles, g.sorted_idx, g.offsets, total, P, scan_scratch, dbg, s)) return 1;
+    // the one host synchronisation of the forward pass (the reference has two:
+    // rasterizer_impl.cu:423,469): the instance count sizes the binning buffers.
+    cudaError_t e = cudaMemcpyAsync(&R, total, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("[CUDA ERROR] reading num_rendered: %s", cudaGetErrorString(e)); return 1; }
+  }
+
+  const size_t bin_bytes = BinState::bytes(R);
+  char* bin_p = binning_alloc(binning_user, bin_bytes > 0 ? bin_bytes : 256);
+  if (!bin_p) { set_error("binning allocation failed"); return 1; }
+  BinState b = BinState::carve(bin_p, R);
+  size_t scratch2_bytes = 0;
+  if (R > 0) {
+    scratch2_bytes = align_up((size_t)R * 4) * 2 + sort_pairs_scratch_bytes(R) + 256;
+    char* sc = scratch_alloc(scratch_user, scratch2_bytes);
+    if (!sc) { set_error("scratch allocation failed"); return 1; }
+    Carver cv(sc);
+    uint32_t* keys_u = cv.take<uint32_t>(R);
+    uint32_t* vals_u = cv.take<uint32_t>(R);
+    char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(R));
+    const int bits = higher_msb((uint32_t)T);
+    const int passes = (bits + 7) / 8;
+    // arrange the ping-pong so that the last pass lands in the persistent binning buffers
+    uint32_t *ka, *va, *kb, *vb;
+    if (passes % 2 == 0) { ka = b.tile_keys; va = b.point_list; kb = keys_u; vb = vals_u; }
+    else { ka = keys_u; va = vals_u; kb = b.tile_keys; vb = b.point_list; }
+    if (launch_emit(p, g, radii, ka, va, s)) return 1;
+    int in_b = 0;
+    if (sort_pairs_u32(ka, va, kb, vb, R, 0, bits, sort_scratch, dbg, s, &in_b)) return 1;
+  }
+  if (launch_tile_ranges(p, R, b.tile_keys, im.ranges, s)) return 1;
+  if (launch_blend_fwd(p, g, b, im, out_color, out_invdepth, s)) return 1;
+
+  if (info) {
+    info->num_rendered = (int32_t)R;
+    info->num_visible = -1;
+    info->geom_bytes = geom_bytes;
+    info->binning_bytes = bin_bytes;
+    info->image_bytes = img_bytes;
+    info->scratch_bytes = scratch1_bytes > scratch2_bytes ? scratch1_bytes : scratch2_bytes;
+  }
+  return 0;
+}
+
+int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
+                 const float* sh, const float* colors_precomp, const float* opacities,
+                 const float* scales, const float* rotations, const float* cov3D_precomp,
+                 const int32_t* radii, const char* geom, const char* binning, const char* image,
+                 const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
+                 float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (validate(prm)) return 1;
+  const DgrParams& p = *prm;
+  if (p.P == 0) return 0;
+  if (!geom || !binning || !image || !dL_dcolor) { set_error("backward: null state or gradient"); return 1; }
+  if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacity) { set_error("backward: null output"); return 1; }
+  if (!scratch_alloc) { set_error("backward: null scratch callback"); return 1; }
+  const size_t P = p.P, N = (size_t)p.W * p.H;
+  const size_t T = (size_t)((p.W + TILE_X - 1) / TILE_X) * ((p.H + TILE_Y - 1) / TILE_Y);
+  GeomState g = GeomState::carve(const_cast<char*>(geom), P);
+  BinState b = BinState::carve(const_cast<char*>(binning), (size_t)num_rendered);
+  ImgState im = ImgState::carve(const_cast<char*>(image), N, T);
+  float* accum = reinterpret_cast<float*>(scratch_alloc(scratch_user, bwd_accum_bytes(P)));
+  if (!accum) { set_error("backward: scratch allocation failed"); return 1; }
+  if (launch_blend_bwd(p, g, b, im, dL_dcolor, dL_dinvdepth_in, accum, s)) return 1;
+  const bool sh_path = colors_precomp == nullptr;
+  return launch_preprocess_bwd(p, means3D, dc, sh, opacities, scales, rotations, cov3D_precomp, radii,
+                               g, accum, dL_dmeans3D, dL_dmeans2D, sh_path ? dL_ddc : nullptr,
+                               sh_path ? dL_dsh : nullptr, dL_dcolors_precomp, dL_dopacity,
+                               cov3D_precomp ? nullptr : dL_dscales,
+                               cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, s);
+}
+
+int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* scales,
+                       const float* rotations, const float* cov3D_precomp, int32_t* radii,
+                       void* stream) {
+  if (!prm || prm->P < 0 || prm->W <= 0 || prm->H <= 0 || !prm->viewmatrix || !prm->projmatrix) {
+    set_error("visible_filter: invalid parameters");
+    return 1;
+  }
+  if (prm->P == 0) return 0;
+  if ((scales == nullptr || rotations == nullptr) == (cov3D_precomp == nullptr)) {
+    set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    return 1;
+  }
+  return launch_filter(*prm, means3D, scales, rotations, cov3D_precomp, radii, (cudaStream_t)stream);
+}
+
+int dgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream) {
+  (void)projmatrix;  // the reference's test only depends on the view-space depth
+  if (P == 0) return 0;
+  if (!means3D || !viewmatrix || !present) { set_error("mark_visible: null pointer"); return 1; }
+  return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+}  // extern "C"

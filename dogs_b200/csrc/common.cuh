@@ -1,0 +1,212 @@
+// Shared helpers for the sm_100a DOGS hot-path kernels.  No torch headers here:
+// every translation unit compiles in seconds with plain nvcc.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/dogs_b200.h"
+
+#define TILE_X 16   // cuda_rasterizer/config.h:16-17
+#define TILE_Y 16
+#define TILE_PIX (TILE_X * TILE_Y)
+
+namespace dogs {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what, bool debug, cudaStream_t s);
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump carving of one caller-allocated buffer.
+struct Carver {
+  char* base; size_t off;
+  explicit Carver(char* b) : base(b), off(0) {}
+  template <typename T> T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off = align_up(off + n * sizeof(T));
+    return p;
+  }
+};
+
+// ---- 3x3 column-major matrix with the multiplication order of GLM 0.9.9.9 --------
+// (m[c][r]; R[c][r] = A[0][r]*B[c][0] + A[1][r]*B[c][1] + A[2][r]*B[c][2],
+//  glm/detail/type_mat3x3.inl:486-519).  The scalar data-flow is kept identical to
+// the reference so that nvcc's FMA contraction produces the same bits.
+struct M3 {
+  float m[3][3];
+};
+__device__ __forceinline__ M3 m3(float a, float b, float c, float d, float e, float f,
+                                 float g, float h, float i) {
+  M3 r;
+  r.m[0][0] = a; r.m[0][1] = b; r.m[0][2] = c;
+  r.m[1][0] = d; r.m[1][1] = e; r.m[1][2] = f;
+  r.m[2][0] = g; r.m[2][1] = h; r.m[2][2] = i;
+  return r;
+}
+__device__ __forceinline__ M3 operator*(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return R;
+}
+__device__ __forceinline__ M3 transpose(const M3& A) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+  return R;
+}
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+__device__ __forceinline__ V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// SH basis constants (cuda_rasterizer/auxiliary.h:21-38)
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+#define SH_C2_0 1.0925484305920792f
+#define SH_C2_1 -1.0925484305920792f
+#define SH_C2_2 0.31539156525252005f
+#define SH_C2_3 -1.0925484305920792f
+#define SH_C2_4 0.5462742152960396f
+#define SH_C3_0 -0.5900435899266435f
+#define SH_C3_1 2.890611442640554f
+#define SH_C3_2 -0.4570457994644658f
+#define SH_C3_3 0.3731763325901154f
+#define SH_C3_4 -0.4570457994644658f
+#define SH_C3_5 1.445305721320277f
+#define SH_C3_6 -0.5900435899266435f
+
+// auxiliary.h:40-43 — the literals are double, so this is evaluated in FP64.
+__device__ __forceinline__ float ndc2Pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// auxiliary.h:69-88
+__device__ __forceinline__ float3 xform4x3(const float3& p, const float* m) {
+  return {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+          m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+          m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]};
+}
+__device__ __forceinline__ float4 xform4x4(const float3& p, const float* m) {
+  return {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+          m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+          m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+          m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]};
+}
+
+// auxiliary.h:45-55
+__device__ __forceinline__ void get_rect(const float2 p, int max_radius, uint2& rmin, uint2& rmax,
+                                         uint32_t gx, uint32_t gy) {
+  rmin = {min(gx, (uint32_t)max((int)0, (int)((p.x - max_radius) / TILE_X))),
+          min(gy, (uint32_t)max((int)0, (int)((p.y - max_radius) / TILE_Y)))};
+  rmax = {min(gx, (uint32_t)max((int)0, (int)((p.x + max_radius + TILE_X - 1) / TILE_X))),
+          min(gy, (uint32_t)max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
+}
+
+// Per-tile reachability test of the key-duplication stage
+// (rasterizer_impl.cu:52-100 max_contrib_power_rect_gaussian_float<15,15> + :151-173).
+// Returns true iff the Gaussian can reach alpha >= 1/255 somewhere in tile (tx,ty).
+__device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mean, int tx, int ty,
+                                               float thr) {
+  const float rminx = (float)(tx * TILE_X), rminy = (float)(ty * TILE_Y);
+  const float rmaxx = (float)((tx + 1) * TILE_X - 1), rmaxy = (float)((ty + 1) * TILE_Y - 1);
+  const float x_min_diff = rminx - mean.x;
+  const float x_left = x_min_diff > 0.0f;
+  const float not_in_x_range = x_left + (mean.x > rmaxx);
+  const float y_min_diff = rminy - mean.y;
+  const float y_above = y_min_diff > 0.0f;
+  const float not_in_y_range = y_above + (mean.y > rmaxy);
+  float max_contrib_power = 0.0f;
+  if ((not_in_y_range + not_in_x_range) > 0.0f) {
+    const float px = x_left * rminx + (1.0f - x_left) * rmaxx;
+    const float py = y_above * rminy + (1.0f - y_above) * rmaxy;
+    const float dx = copysignf(float(TILE_X - 1), x_min_diff);
+    const float dy = copysignf(float(TILE_Y - 1), y_min_diff);
+    const float diffx = mean.x - px;
+    const float diffy = mean.y - py;
+    const float rcp_dxdxcox = __frcp_rn((uint32_t)((TILE_X - 1) * (TILE_X - 1)) * co.x);
+    const float rcp_dydycoz = __frcp_rn((uint32_t)((TILE_Y - 1) * (TILE_Y - 1)) * co.z);
+    const float tx_ = not_in_y_range * __saturatef((dx * co.x * diffx + dx * co.y * diffy) * rcp_dxdxcox);
+    const float ty_ = not_in_x_range * __saturatef((dy * co.y * diffx + dy * co.z * diffy) * rcp_dydycoz);
+    const float mx = px + tx_ * dx, my = py + ty_ * dy;
+    const float ddx = mean.x - mx, ddy = mean.y - my;
+    max_contrib_power = 0.5f * (co.x * ddx * ddx + co.z * ddy * ddy) + co.y * ddx * ddy;
+  }
+  return max_contrib_power <= thr;
+}
+
+// Internal per-Gaussian record written by preprocess and gathered by the blend kernels.
+// a = {conic.x, conic.y, conic.z, opacity}, b = {x, y, 1/depth, r}, c = {g, b, depth, unused}
+struct __align__(16) SplatRecord { float4 a, b, c; };
+
+// ---- stage launchers (defined in the .cu files) -----------------------------------
+struct GeomState {
+  SplatRecord* rec; uint8_t* clamped; uint32_t* tiles; uint32_t* depth_key;
+  uint32_t* sorted_idx;    // Gaussian ids in depth order
+  uint32_t* offsets;       // exclusive scan of tiles in depth order
+  static size_t bytes(size_t P);
+  static GeomState carve(char* p, size_t P);
+};
+struct BinState {
+  uint32_t* point_list; uint32_t* tile_keys;
+  static size_t bytes(size_t R);
+  static BinState carve(char* p, size_t R);
+};
+struct ImgState {
+  uint2* ranges; float* final_T; uint32_t* n_contrib;
+  float* pix_color; float* pix_invdepth;  // forward outputs kept for the backward replay
+  static size_t bytes(size_t N, size_t T);
+  static ImgState carve(char* p, size_t N, size_t T);
+};
+
+// radix_sort.cu
+size_t sort_pairs_scratch_bytes(size_t n);
+// Stable LSD sort of (key,val) u32 pairs on bits [begin_bit,end_bit), 8 bits per pass, ping-pong
+// between the (a) and (b) buffers starting from (a); *result_in_b tells where the result is.
+int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                   size_t n, int begin_bit, int end_bit, char* scratch, bool debug, cudaStream_t s,
+                   int* result_in_b);
+void launch_iota(uint32_t* out, size_t n, cudaStream_t s);
+size_t scan_scratch_bytes(size_t n);
+// out[i] = sum_{j<i} in[idx ? idx[j] : j]; total (may be null) receives the grand total.
+int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* total,
+                       size_t n, char* scratch, bool debug, cudaStream_t s);
+
+
+// rasterizer_fwd.cu
+int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const float* dc,
+                          const float* sh, const float* colors_precomp, const float* opacities,
+                          const float* scales, const float* rotations, const float* cov3D_precomp,
+                          int32_t* radii, GeomState& g, cudaStream_t s);
+int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
+                uint32_t* vals, cudaStream_t s);
+int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,
+                       cudaStream_t s);
+int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
+                     float* out_color, float* out_invdepth, cudaStream_t s);
+int launch_filter(const DgrParams& prm, const float* means3D, const float* scales,
+                  const float* rotations, const float* cov3D_precomp, int32_t* radii, cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
+                        cudaStream_t s);
+// rasterizer_bwd.cu
+size_t bwd_accum_bytes(size_t P);
+int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
+                     const float* dL_dcolor, const float* dL_dinvdepth, float* accum,
+                     cudaStream_t s);
+int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const float* dc,
+                          const float* sh, const float* opacities, const float* scales,
+                          const float* rotations, const float* cov3D_precomp, const int32_t* radii,
+                          const GeomState& g, const float* accum, float* dL_dmeans3D,
+                          float* dL_dmeans2D, float* dL_ddc, float* dL_dsh,
+                          float* dL_dcolors_precomp, float* dL_dopacity, float* dL_dscales,
+                          float* dL_drotations, float* dL_dcov3D, cudaStream_t s);
+
+}  // namespace dogs

@@ -1,0 +1,278 @@
+// Stable LSD radix sort of (u32 key, u32 value) pairs and an exclusive scan, written for the
+// binning stage of the rasterizer.  They replace cub::DeviceRadixSort::SortPairs /
+// cub::DeviceScan::InclusiveSum at rasterizer_impl.cu:419,447-452,467 and simple_knn.cu:210-213.
+//
+// Design for B200: the reference sorts R 64-bit (tile|depth) keys in 6 digit passes.  Here depth
+// order is established once per Gaussian (P elements, 4 passes of 8 bits) and instances are
+// emitted in that order, so only a stable sort by tile id (12-13 bits => 2 passes over 4-byte
+// keys) touches the R-sized arrays.  Each pass is histogram -> row scan -> ranked scatter; the
+// scatter writes straight to global memory because the destination arrays (<= 68 MB each at
+// R = 17 M) sit in the 126 MB L2, which merges the 4-byte stores into full sectors before they
+// reach HBM.  No kernel ever waits on another CTA.
+#include "common.cuh"
+
+namespace dogs {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX = 256;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
+                  uint32_t* __restrict__ hist, uint32_t nblk) {
+  __shared__ uint32_t h[RADIX];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * SORT_CHUNK;
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    uint32_t idx = base + i * SORT_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// One CTA per digit: exclusive scan of that digit's per-block counts, digit total to totals[d].
+__global__ void __launch_bounds__(256)
+radix_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblk, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t wsum[8];
+  __shared__ uint32_t carry_s;
+  uint32_t* row = hist + (size_t)blockIdx.x * nblk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < nblk; start += 256) {
+    uint32_t i = start + threadIdx.x;
+    uint32_t v = i < nblk ? row[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < warp) woff += wsum[w];
+    uint32_t carry = carry_s;
+    if (i < nblk) row[i] = carry + woff + x - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = carry + woff + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                     int shift, uint32_t mask, const uint32_t* __restrict__ hist, uint32_t nblk,
+                     const uint32_t* __restrict__ totals) {
+  __shared__ uint32_t cnt[SORT_WARPS][RADIX];
+  __shared__ uint32_t wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < SORT_WARPS; w++) cnt[w][threadIdx.x] = 0;
+
+  // digit base = exclusive scan of the digit totals (thread d owns digit d)
+  uint32_t tot = totals[threadIdx.x];
+  uint32_t x = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  uint32_t dbase = x - tot;
+#pragma unroll
+  for (int w = 0; w < 8; w++) if (w < warp) dbase += wsum[w];
+
+  // Warp w ranks the contiguous slice [base + w*512, +512) in order, 32 keys per step.
+  const uint32_t wbase = blockIdx.x * SORT_CHUNK + warp * (32 * SORT_ITEMS);
+  uint32_t key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+  for (int s = 0; s < SORT_ITEMS; s++) {
+    uint32_t idx = wbase + s * 32 + lane;
+    key[s] = idx < n ? keys_in[idx] : 0u;
+  }
+#pragma unroll
+  for (int s = 0; s < SORT_ITEMS; s++) {
+    uint32_t idx = wbase + s * 32 + lane;
+    bool valid = idx < n;
+    uint32_t d = valid ? ((key[s] >> shift) & mask) : 0xffffffffu;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = cnt[warp][d];
+      cnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[s] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    uint32_t run = hist[threadIdx.x * nblk + blockIdx.x] + dbase;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+      uint32_t t = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < SORT_ITEMS; s++) {
+    uint32_t idx = wbase + s * 32 + lane;
+    if (idx < n) {
+      uint32_t d = (key[s] >> shift) & mask;
+      uint32_t dst = cnt[warp][d] + rank[s];
+      keys_out[dst] = key[s];
+      vals_out[dst] = vals_in[idx];
+    }
+  }
+}
+
+__global__ void iota_kernel(uint32_t* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+void launch_iota(uint32_t* out, size_t n, cudaStream_t s) {
+  if (n) iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, (uint32_t)n);
+}
+
+size_t sort_pairs_scratch_bytes(size_t n) {
+  size_t nblk = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+  if (nblk == 0) nblk = 1;
+  return align_up(nblk * RADIX * sizeof(uint32_t)) + align_up(RADIX * sizeof(uint32_t));
+}
+
+int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                   size_t n, int begin_bit, int end_bit, char* scratch, bool debug,
+                   cudaStream_t s, int* result_in_b) {
+  *result_in_b = 0;
+  if (n == 0 || end_bit <= begin_bit) return 0;
+  uint32_t nblk = (uint32_t)((n + SORT_CHUNK - 1) / SORT_CHUNK);
+  Carver cv(scratch);
+  uint32_t* hist = cv.take<uint32_t>((size_t)nblk * RADIX);
+  uint32_t* totals = cv.take<uint32_t>(RADIX);
+  uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+  for (int b = begin_bit; b < end_bit; b += 8) {
+    int nb = end_bit - b < 8 ? end_bit - b : 8;
+    uint32_t mask = (1u << nb) - 1u;
+    radix_hist_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, (uint32_t)n, b, mask, hist, nblk);
+    radix_rowscan_kernel<<<RADIX, 256, 0, s>>>(hist, nblk, totals);
+    radix_scatter_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, vi, ko, vo, (uint32_t)n, b, mask, hist,
+                                                      nblk, totals);
+    if (int e = check_launch("radix pass", debug, s)) return e;
+    uint32_t* t;
+    t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+    *result_in_b ^= 1;
+  }
+  return 0;
+}
+
+// ---- exclusive scan -----------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* wsum, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  uint32_t woff = 0, t = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++) {
+    uint32_t ws = wsum[w];
+    if (w < warp) woff += ws;
+    t += ws;
+  }
+  *total = t;
+  __syncthreads();
+  return woff + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ idx, uint32_t n,
+                   uint32_t* __restrict__ partial) {
+  __shared__ uint32_t wsum[SCAN_THREADS / 32];
+  uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS, sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t j = base + i;
+    if (j < n) sum += in[idx ? idx[j] : j];
+  }
+  uint32_t total;
+  block_exclusive_scan(sum, wsum, &total);
+  if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_spine_kernel(uint32_t* __restrict__ partial, uint32_t nb, uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t wsum[SCAN_THREADS / 32];
+  uint32_t carry = 0;
+  for (uint32_t start = 0; start < nb; start += SCAN_THREADS) {
+    uint32_t i = start + threadIdx.x;
+    uint32_t v = i < nb ? partial[i] : 0, tot;
+    uint32_t ex = block_exclusive_scan(v, wsum, &tot);
+    if (i < nb) partial[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ idx, uint32_t n,
+                  const uint32_t* __restrict__ partial, uint32_t* __restrict__ out) {
+  __shared__ uint32_t wsum[SCAN_THREADS / 32];
+  uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t j = base + i;
+    v[i] = j < n ? in[idx ? idx[j] : j] : 0;
+    sum += v[i];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(sum, wsum, &total) + partial[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t j = base + i;
+    if (j < n) out[j] = ex;
+    ex += v[i];
+  }
+}
+
+size_t scan_scratch_bytes(size_t n) {
+  return align_up(((n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * sizeof(uint32_t));
+}
+
+int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* total,
+                       size_t n, char* scratch, bool debug, cudaStream_t s) {
+  if (n == 0) {
+    if (total) cudaMemsetAsync(total, 0, sizeof(uint32_t), s);
+    return 0;
+  }
+  uint32_t nb = (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  uint32_t* partial = reinterpret_cast<uint32_t*>(scratch);
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial);
+  scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(partial, nb, total);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial, out);
+  return check_launch("exclusive scan", debug, s);
+}
+
+}  // namespace dogs

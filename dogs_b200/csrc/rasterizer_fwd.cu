@@ -1,0 +1,494 @@
+// Forward rasterizer kernels (sm_100a): per-Gaussian preprocess with the per-tile reachability
+// cull folded in, instance emission in depth order, tile ranges, and the per-tile front-to-back
+// alpha blend.  Arithmetic follows cuda_rasterizer/forward.cu:24-276,349-501 and
+// rasterizer_impl.cu:52-220 operation by operation so that radii, keys,
+// ranges, n_contrib and final_T come out bit-identical; the kernel structure does not.
+#include "common.cuh"
+
+namespace dogs {
+
+constexpr int PRE_THREADS = 128;
+
+// ---- forward.cu:119-153 ----------------------------------------------------------
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot,
+                                                    float* cov3D) {
+  M3 S = m3(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
+  S.m[0][0] = mod * scale.x;
+  S.m[1][1] = mod * scale.y;
+  S.m[2][2] = mod * scale.z;
+  float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+  M3 R = m3(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+            2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+            2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+  M3 M = S * R;
+  M3 Sigma = transpose(M) * M;
+  cov3D[0] = Sigma.m[0][0];
+  cov3D[1] = Sigma.m[0][1];
+  cov3D[2] = Sigma.m[0][2];
+  cov3D[3] = Sigma.m[1][1];
+  cov3D[4] = Sigma.m[1][2];
+  cov3D[5] = Sigma.m[2][2];
+}
+
+// ---- forward.cu:79-114 -----------------------------------------------------------
+__device__ __forceinline__ float3 cov2d_from_cov3d(const float3& mean, float focal_x, float focal_y,
+                                                  float tan_fovx, float tan_fovy,
+                                                  const float* cov3D, const float* view) {
+  float3 t = xform4x3(mean, view);
+  const float limx = 1.3f * tan_fovx;
+  const float limy = 1.3f * tan_fovy;
+  const float txtz = t.x / t.z;
+  const float tytz = t.y / t.z;
+  t.x = min(limx, max(-limx, txtz)) * t.z;
+  t.y = min(limy, max(-limy, tytz)) * t.z;
+  M3 J = m3(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z),
+            0.0f, focal_y / t.z, -(focal_y * t.y) / (t.z * t.z),
+            0, 0, 0);
+  M3 Wm = m3(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
+  M3 T = Wm * J;
+  M3 Vrk = m3(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4],
+              cov3D[5]);
+  M3 cov = transpose(T) * transpose(Vrk) * T;
+  return {cov.m[0][0], cov.m[0][1], cov.m[1][1]};
+}
+
+// ---- forward.cu:24-76 ------------------------------------------------------------
+// sh points at this Gaussian's M "rest" coefficients (row of 3*M floats, any address space).
+__device__ __forceinline__ V3 color_from_sh(int deg, V3 pos, V3 campos, V3 dc, const float* sh,
+                                            uint32_t& clamped) {
+  V3 dir = pos - campos;
+  dir = dir / sqrtf(dot(dir, dir));
+  V3 result = SH_C0 * dc;
+#define SHV(i) (V3{sh[3 * (i)], sh[3 * (i) + 1], sh[3 * (i) + 2]})
+  if (deg > 0) {
+    float x = dir.x, y = dir.y, z = dir.z;
+    result = result - SH_C1 * y * SHV(0) + SH_C1 * z * SHV(1) - SH_C1 * x * SHV(2);
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      result = result + SH_C2_0 * xy * SHV(3) + SH_C2_1 * yz * SHV(4) +
+               SH_C2_2 * (2.0f * zz - xx - yy) * SHV(5) + SH_C2_3 * xz * SHV(6) +
+               SH_C2_4 * (xx - yy) * SHV(7);
+      if (deg > 2) {
+        result = result + SH_C3_0 * y * (3.0f * xx - yy) * SHV(8) + SH_C3_1 * xy * z * SHV(9) +
+                 SH_C3_2 * y * (4.0f * zz - xx - yy) * SHV(10) +
+                 SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHV(11) +
+                 SH_C3_4 * x * (4.0f * zz - xx - yy) * SHV(12) + SH_C3_5 * z * (xx - yy) * SHV(13) +
+                 SH_C3_6 * x * (xx - 3.0f * yy) * SHV(14);
+      }
+    }
+  }
+#undef SHV
+  result.x += 0.5f;
+  result.y += 0.5f;
+  result.z += 0.5f;
+  clamped = (result.x < 0 ? 1u : 0u) | (result.y < 0 ? 2u : 0u) | (result.z < 0 ? 4u : 0u);
+  return {fmaxf(result.x, 0.0f), fmaxf(result.y, 0.0f), fmaxf(result.z, 0.0f)};
+}
+
+// One thread per Gaussian.  The CTA's slice of the SH tensor (the bulk of the input bytes:
+// 180 of 236 B per Gaussian) is contiguous, so it is staged into shared memory with coalesced
+// 16-byte loads and read back row-wise at a stride of 3*M floats (odd => conflict-free).
+// Replaces preprocessCUDA (forward.cu:156-276) and the counting half of duplicateWithKeys
+// (rasterizer_impl.cu:120-190): tiles[idx] is the number of instances that survive the cull.
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
+                      const float* __restrict__ scales, float scale_modifier,
+                      const float* __restrict__ rotations, const float* __restrict__ opacities,
+                      const float* __restrict__ dc, const float* __restrict__ shs,
+                      const float* __restrict__ cov3D_precomp,
+                      const float* __restrict__ colors_precomp, const float* __restrict__ view,
+                      const float* __restrict__ proj, const float* __restrict__ cam_pos, int W,
+                      int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
+                      int* __restrict__ radii, SplatRecord* __restrict__ rec,
+                      uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
+                      uint32_t* __restrict__ depth_key, uint32_t gx, uint32_t gy, bool prefiltered,
+                      bool antialiasing) {
+  extern __shared__ float4 sh_stage4[];
+  float* sh_stage = reinterpret_cast<float*>(sh_stage4);
+  const int first = blockIdx.x * PRE_THREADS;
+  const int idx = first + threadIdx.x;
+  const bool use_sh = (colors_precomp == nullptr) && D > 0 && M > 0;
+  if (use_sh) {
+    const int count = min(PRE_THREADS, P - first);
+    const size_t nfl = (size_t)count * 3 * M;
+    const float* src = shs + (size_t)first * 3 * M;
+    if ((((uintptr_t)src) & 15) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(src);
+      const size_t n4 = nfl >> 2;
+      for (size_t i = threadIdx.x; i < n4; i += PRE_THREADS) sh_stage4[i] = __ldg(src4 + i);
+      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PRE_THREADS) sh_stage[i] = __ldg(src + i);
+    } else {
+      for (size_t i = threadIdx.x; i < nfl; i += PRE_THREADS) sh_stage[i] = __ldg(src + i);
+    }
+    __syncthreads();
+  }
+  if (idx >= P) return;
+
+  int radius_out = 0;
+  uint32_t ntiles = 0, dkey = 0xffffffffu;
+  do {
+    float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    // auxiliary.h:150-175 in_frustum
+    float4 p_hom = xform4x4(p_orig, proj);
+    float p_w = 1.0f / (p_hom.w + 0.0000001f);
+    float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+    float3 p_view = xform4x3(p_orig, view);
+    if (p_view.z <= 0.2f) {
+      if (prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+      break;
+    }
+    float cov3D[6];
+    if (cov3D_precomp != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
+    } else {
+      float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+      float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+      cov3d_from_scale_rot(sc, scale_modifier, q, cov3D);
+    }
+    float3 cov = cov2d_from_cov3d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
+
+    constexpr float h_var = 0.3f;
+    const float det_cov = cov.x * cov.z - cov.y * cov.y;
+    cov.x += h_var;
+    cov.z += h_var;
+    const float det_cov_plus_h_cov = cov.x * cov.z - cov.y * cov.y;
+    float h_convolution_scaling = 1.0f;
+    if (antialiasing) h_convolution_scaling = sqrt(max(0.000025f, det_cov / det_cov_plus_h_cov));
+    const float det = det_cov_plus_h_cov;
+    if (det == 0.0f) break;
+    float det_inv = 1.f / det;
+    float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+    float mid = 0.5f * (cov.x + cov.z);
+    float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+    float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+    float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+    float2 point_image = {ndc2Pix(p_proj.x, W), ndc2Pix(p_proj.y, H)};
+    uint2 rect_min, rect_max;
+    get_rect(point_image, (int)my_radius, rect_min, rect_max, gx, gy);
+    if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) break;
+
+    float3 rgb;
+    uint32_t clamped = 0;
+    if (colors_precomp == nullptr) {
+      V3 pos = {p_orig.x, p_orig.y, p_orig.z};
+      V3 cp = {cam_pos[0], cam_pos[1], cam_pos[2]};
+      V3 d0 = {dc[3 * idx], dc[3 * idx + 1], dc[3 * idx + 2]};
+      V3 c = color_from_sh(D, pos, cp, d0, sh_stage + (size_t)threadIdx.x * 3 * M, clamped);
+      rgb = {c.x, c.y, c.z};
+    } else {
+      rgb = {colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]};
+    }
+    clamped_out[idx] = (uint8_t)clamped;
+
+    const float depth = p_view.z;
+    const float opacity = opacities[idx] * h_convolution_scaling;
+    radius_out = (int)my_radius;
+    const float4 co = {conic.x, conic.y, conic.z, opacity};
+    SplatRecord r;
+    r.a = co;
+    r.b = {point_image.x, point_image.y, 1.f / depth, rgb.x};
+    r.c = {rgb.y, rgb.z, depth, 0.f};
+    rec[idx] = r;
+
+    // rasterizer_impl.cu:151-177: count the tiles of the rect the Gaussian can actually reach.
+    const float thr = logf(co.w / (1.0f / 255.0f));
+    for (int y = rect_min.y; y < (int)rect_max.y; y++)
+      for (int x = rect_min.x; x < (int)rect_max.x; x++)
+        ntiles += tile_reachable(co, point_image, x, y, thr) ? 1u : 0u;
+    dkey = __float_as_uint(depth);
+  } while (0);
+  radii[idx] = radius_out;
+  tiles[idx] = ntiles;
+  depth_key[idx] = ntiles ? dkey : 0xffffffffu;
+}
+
+// One thread per depth-sorted position: re-walk the rect and write (tile id, Gaussian id) for
+// every reachable tile (the emitting half of duplicateWithKeys).  Instances are therefore
+// already in (depth, Gaussian id) order; the stable sort by tile id that follows reproduces the
+// order of the reference's 64-bit (tile|depth) sort without ever materialising 64-bit keys.
+__global__ void __launch_bounds__(256)
+emit_instances_kernel(int P, const uint32_t* __restrict__ sorted_idx,
+                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ tiles,
+                      const SplatRecord* __restrict__ rec, const int* __restrict__ radii,
+                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, uint32_t gx,
+                      uint32_t gy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const uint32_t idx = sorted_idx[i];
+  if (tiles[idx] == 0) return;
+  uint32_t off = offsets[i];
+  const float4 co = rec[idx].a;
+  const float4 b = rec[idx].b;
+  const float2 xy = {b.x, b.y};
+  uint2 rect_min, rect_max;
+  get_rect(xy, radii[idx], rect_min, rect_max, gx, gy);
+  const float thr = logf(co.w / (1.0f / 255.0f));
+  for (int y = rect_min.y; y < (int)rect_max.y; y++)
+    for (int x = rect_min.x; x < (int)rect_max.x; x++)
+      if (tile_reachable(co, xy, x, y, thr)) {
+        tile_keys[off] = y * gx + x;
+        vals[off] = idx;
+        off++;
+      }
+}
+
+// identifyTileRanges (rasterizer_impl.cu:195-220) on 32-bit tile keys; no pad entries exist.
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys, uint2* __restrict__ ranges) {
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  uint32_t cur = tile_keys[idx];
+  if (idx == 0)
+    ranges[cur].x = 0;
+  else {
+    uint32_t prev = tile_keys[idx - 1];
+    if (cur != prev) {
+      ranges[prev].y = idx;
+      ranges[cur].x = idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = L;
+}
+
+// ---- blend ------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// One CTA per 16x16 tile, one thread per pixel (renderCUDA, forward.cu:349-501).  Batches of 256
+// records are gathered global->shared with cp.async into a double buffer, so the gather of batch
+// i+1 overlaps the blend of batch i.  No per-bucket state is written: the backward replays the
+// blend front to back from final_T / n_contrib (see rasterizer_bwd.cu).
+__global__ void __launch_bounds__(TILE_PIX)
+blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
+                 int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
+                 float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                 float* __restrict__ out_color, float* __restrict__ invdepth,
+                 float* __restrict__ pix_color, float* __restrict__ pix_invdepth) {
+  __shared__ float4 sA[2][TILE_PIX];
+  __shared__ float4 sB[2][TILE_PIX];
+  __shared__ float4 sC[2][TILE_PIX];
+  const uint32_t tid = threadIdx.y * TILE_X + threadIdx.x;
+  const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+  const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
+  const uint32_t pix_id = W * pix.y + pix.x;
+  const float2 pixf = {(float)pix.x, (float)pix.y};
+  const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+  bool done = !inside;
+
+  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+  const int rounds = ((range.y - range.x + TILE_PIX - 1) / TILE_PIX);
+  int toDo = range.y - range.x;
+
+  float T = 1.0f;
+  uint32_t contributor = 0, last_contributor = 0;
+  float C[3] = {0.f, 0.f, 0.f};
+  float expected_invdepth = 0.0f;
+
+  auto fetch = [&](int round, int buf) {
+    uint32_t progress = range.x + round * TILE_PIX + tid;
+    if (progress < range.y) {
+      const SplatRecord* r = rec + point_list[progress];
+      cp_async16(&sA[buf][tid], &r->a);
+      cp_async16(&sB[buf][tid], &r->b);
+      cp_async16(&sC[buf][tid], &r->c);
+    }
+    cp_async_commit();
+  };
+  if (rounds > 0) fetch(0, 0);
+
+  for (int i = 0; i < rounds; i++, toDo -= TILE_PIX) {
+    const int buf = i & 1;
+    // forward.cu:415-417 (the barrier also frees buffer buf^1, last read in round i-1)
+    int num_done = __syncthreads_count(done);
+    if (num_done == TILE_PIX) break;
+    if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    for (int j = 0; !done && j < min(TILE_PIX, toDo); j++) {
+      contributor++;
+      const float4 con_o = sA[buf][j];
+      const float4 b = sB[buf][j];
+      float2 xy = {b.x, b.y};
+      float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+      float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+      if (power > 0.0f) continue;
+      float alpha = min(0.99f, con_o.w * exp(power));
+      if (alpha < 1.0f / 255.0f) continue;
+      float test_T = T * (1 - alpha);
+      if (test_T < 0.0001f) {
+        done = true;
+        continue;
+      }
+      const float4 c = sC[buf][j];
+      C[0] += b.w * alpha * T;
+      C[1] += c.x * alpha * T;
+      C[2] += c.y * alpha * T;
+      expected_invdepth += b.z * alpha * T;
+      T = test_T;
+      last_contributor = contributor;
+    }
+  }
+  cp_async_wait<0>();
+
+  if (inside) {
+    final_T[pix_id] = T;
+    n_contrib[pix_id] = last_contributor;
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      const float v = C[ch] + T * bg_color[ch];
+      out_color[ch * HW + pix_id] = v;
+      pix_color[ch * HW + pix_id] = v;  // rasterizer_impl.cu:495-496 (copy kept for backward)
+    }
+    invdepth[pix_id] = expected_invdepth;
+    pix_invdepth[pix_id] = expected_invdepth;
+  }
+}
+
+// ---- visible_filter / mark_visible ---------------------------------------------------
+// filter_preprocessCUDA (forward.cu:279-344): radii only, without the +0.3 low-pass.
+__global__ void __launch_bounds__(256)
+filter_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ scales,
+              float scale_modifier, const float* __restrict__ rotations,
+              const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
+              const float* __restrict__ proj, int W, int H, float tan_fovx, float tan_fovy,
+              float focal_x, float focal_y, int* __restrict__ radii, uint32_t gx, uint32_t gy,
+              bool prefiltered) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  int radius_out = 0;
+  do {
+    float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    float4 p_hom = xform4x4(p_orig, proj);
+    float p_w = 1.0f / (p_hom.w + 0.0000001f);
+    float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+    float3 p_view = xform4x3(p_orig, view);
+    if (p_view.z <= 0.2f) {
+      if (prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+      break;
+    }
+    float cov3D[6];
+    if (cov3D_precomp != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
+    } else {
+      float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+      float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+      cov3d_from_scale_rot(sc, scale_modifier, q, cov3D);
+    }
+    float3 cov = cov2d_from_cov3d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
+    float det = (cov.x * cov.z - cov.y * cov.y);
+    if (det == 0.0f) break;
+    float mid = 0.5f * (cov.x + cov.z);
+    float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+    float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+    float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+    float2 point_image = {ndc2Pix(p_proj.x, W), ndc2Pix(p_proj.y, H)};
+    uint2 rect_min, rect_max;
+    get_rect(point_image, (int)my_radius, rect_min, rect_max, gx, gy);
+    if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) break;
+    radius_out = (int)my_radius;
+  } while (0);
+  radii[idx] = radius_out;
+}
+
+// checkFrustum (rasterizer_impl.cu:104-116)
+__global__ void __launch_bounds__(256)
+mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                    uint8_t* __restrict__ present) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+  float3 p_view = xform4x3(p, view);
+  present[idx] = p_view.z > 0.2f ? 1 : 0;
+}
+
+// ---- host-side stage launchers ---------------------------------------------------------
+int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const float* dc,
+                          const float* sh, const float* colors_precomp, const float* opacities,
+                          const float* scales, const float* rotations, const float* cov3D_precomp,
+                          int32_t* radii, GeomState& g, cudaStream_t s) {
+  const float focal_y = prm.H / (2.0f * prm.tanfovy);
+  const float focal_x = prm.W / (2.0f * prm.tanfovx);
+  const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
+  const bool use_sh = colors_precomp == nullptr && prm.D > 0 && prm.M > 0;
+  size_t smem = use_sh ? (size_t)PRE_THREADS * 3 * prm.M * sizeof(float) + 16 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  if (smem > 96 * 1024) {
+    set_error("preprocess: SH row too large (M=%d)", prm.M);
+    return 1;
+  }
+  preprocess_fwd_kernel<<<(prm.P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, s>>>(
+      prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
+      cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
+      prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
+      gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
+  return check_launch("preprocess_fwd", prm.debug != 0, s);
+}
+
+int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
+                uint32_t* vals, cudaStream_t s) {
+  const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
+  emit_instances_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_idx, g.offsets, g.tiles,
+                                                            g.rec, radii, tile_keys, vals, gx, gy);
+  return check_launch("emit_instances", prm.debug != 0, s);
+}
+
+int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,
+                       cudaStream_t s) {
+  const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
+  cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
+  if (R > 0) tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, ranges);
+  return check_launch("tile_ranges", prm.debug != 0, s);
+}
+
+int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
+                     float* out_color, float* out_invdepth, cudaStream_t s) {
+  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
+  dim3 block(TILE_X, TILE_Y, 1);
+  blend_fwd_kernel<<<grid, block, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+                                          im.final_T, im.n_contrib, out_color, out_invdepth,
+                                          im.pix_color, im.pix_invdepth);
+  return check_launch("blend_fwd", prm.debug != 0, s);
+}
+
+int launch_filter(const DgrParams& prm, const float* means3D, const float* scales,
+                  const float* rotations, const float* cov3D_precomp, int32_t* radii,
+                  cudaStream_t s) {
+  const float focal_y = prm.H / (2.0f * prm.tanfovy);
+  const float focal_x = prm.W / (2.0f * prm.tanfovx);
+  const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
+  filter_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(
+      prm.P, means3D, scales, prm.scale_modifier, rotations, cov3D_precomp, prm.viewmatrix,
+      prm.projmatrix, prm.W, prm.H, prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, gx, gy,
+      prm.prefiltered != 0);
+  return check_launch("visible_filter", prm.debug != 0, s);
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
+                        cudaStream_t s) {
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+  return check_launch("mark_visible", false, s);
+}
+
+}  // namespace dogs

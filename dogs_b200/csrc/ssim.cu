@@ -1,0 +1,205 @@
+// fused-SSIM forward / backward (submodules/fused-ssim/ssim.cu:187-366).
+//
+// The reference runs 5 (forward) / 3 (backward) separable 11-tap convolutions one after the other
+// through a single scratch tile: 18 / 15 block-wide barriers per channel and a scratch re-zero
+// before every convolution.  Here all statistics of a 32x32 output tile are produced in ONE
+// horizontal and ONE vertical pass (3 barriers per tile), one (batch, channel) plane per
+// blockIdx.z.  Tap order and the rounding points (products rounded before the tap FMA,
+// `conv - mu*mu`) follow the reference, so results agree to the last bits.
+#include "common.cuh"
+
+namespace dogs {
+
+constexpr int SS_BX = 32, SS_BY = 32, SS_R = 5;
+constexpr int SS_SX = SS_BX + 2 * SS_R;   // 42
+constexpr int SS_SY = SS_BY + 2 * SS_R;   // 42
+constexpr int SS_PAD = SS_SX + 1;         // 43: odd row pitch
+constexpr int SS_THREADS = 256;
+
+__constant__ float SS_G[11] = {0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f,
+                               0.10936068743467331f,  0.21300552785396576f,   0.26601171493530273f,
+                               0.21300552785396576f,  0.10936068743467331f,   0.036000773310661316f,
+                               0.0075987582094967365f, 0.001028380123898387f};
+
+__device__ __forceinline__ float pix_or_zero(const float* __restrict__ plane, int y, int x, int H,
+                                             int W) {
+  return (x >= W || y >= H || x < 0 || y < 0) ? 0.0f : plane[(size_t)y * W + x];
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+fssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img1,
+                 const float* __restrict__ img2, float* __restrict__ ssim_map,
+                 float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
+                 float* __restrict__ dm_dsigma12) {
+  __shared__ float p1[SS_SY][SS_PAD];
+  __shared__ float p2[SS_SY][SS_PAD];
+  __shared__ float xc[5][SS_SY][SS_BX];
+  const int tid = threadIdx.x;
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const float* a = img1 + plane;
+  const float* b = img2 + plane;
+  const int y0 = blockIdx.y * SS_BY - SS_R, x0 = blockIdx.x * SS_BX - SS_R;
+  for (int t = tid; t < SS_SY * SS_SX; t += SS_THREADS) {
+    const int ly = t / SS_SX, lx = t % SS_SX;
+    p1[ly][lx] = pix_or_zero(a, y0 + ly, x0 + lx, H, W);
+    p2[ly][lx] = pix_or_zero(b, y0 + ly, x0 + lx, H, W);
+  }
+  __syncthreads();
+  for (int t = tid; t < SS_SY * SS_BX; t += SS_THREADS) {
+    const int ly = t / SS_BX, lx = t % SS_BX;
+    float mu1 = 0.f, s11 = 0.f, mu2 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float u = p1[ly][lx + k], v = p2[ly][lx + k];
+      const float g = SS_G[k];
+      mu1 += g * u;
+      s11 += g * (u * u);
+      mu2 += g * v;
+      s22 += g * (v * v);
+      s12 += g * (u * v);
+    }
+    xc[0][ly][lx] = mu1; xc[1][ly][lx] = s11; xc[2][ly][lx] = mu2; xc[3][ly][lx] = s22; xc[4][ly][lx] = s12;
+  }
+  __syncthreads();
+  const int lx = tid & 31;
+  const int px = blockIdx.x * SS_BX + lx;
+#pragma unroll
+  for (int r = 0; r < SS_BY / (SS_THREADS / 32); r++) {
+    const int ly = (tid >> 5) + r * (SS_THREADS / 32);
+    const int py = blockIdx.y * SS_BY + ly;
+    float q[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      float val = 0.f;
+#pragma unroll
+      for (int k = 0; k < 11; k++) val += SS_G[k] * xc[c][ly + k][lx];
+      q[c] = val;
+    }
+    const float mu1 = q[0];
+    const float sigma1_sq = q[1] - mu1 * mu1;
+    const float mu2 = q[2];
+    const float sigma2_sq = q[3] - mu2 * mu2;
+    const float sigma12 = q[4] - mu1 * mu2;
+    const float mu1_sq = mu1 * mu1;
+    const float mu2_sq = mu2 * mu2;
+    const float mu1_mu2 = mu1 * mu2;
+    const float C = (2.0f * mu1_mu2 + C1);
+    const float D = (2.0f * sigma12 + C2);
+    const float A = (mu1_sq + mu2_sq + C1);
+    const float B = (sigma1_sq + sigma2_sq + C2);
+    const float m = (C * D) / (A * B);
+    if (px < W && py < H) {
+      const size_t gi = plane + (size_t)py * W + px;
+      ssim_map[gi] = m;
+      if (dm_dmu1) {
+        dm_dmu1[gi] = ((mu2 * 2.0f * D) / (A * B) - (mu2 * 2.0f * C) / (A * B) -
+                       (mu1 * 2.0f * C * D) / (A * A * B) + (mu1 * 2.0f * C * D) / (A * B * B));
+        dm_dsigma1_sq[gi] = ((-C * D) / (A * B * B));
+        dm_dsigma12[gi] = ((2 * C) / (A * B));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+fssim_bwd_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
+                 const float* __restrict__ dL_dmap, const float* __restrict__ dm_dmu1,
+                 const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
+                 float* __restrict__ dL_dimg1) {
+  __shared__ float t1[SS_SY][SS_PAD];
+  __shared__ float t2[SS_SY][SS_PAD];
+  __shared__ float t3[SS_SY][SS_PAD];
+  __shared__ float xc[3][SS_SY][SS_BX];
+  const int tid = threadIdx.x;
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const int y0 = blockIdx.y * SS_BY - SS_R, x0 = blockIdx.x * SS_BX - SS_R;
+  for (int t = tid; t < SS_SY * SS_SX; t += SS_THREADS) {
+    const int ly = t / SS_SX, lx = t % SS_SX;
+    const int y = y0 + ly, x = x0 + lx;
+    float dl = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    if (!(x >= W || y >= H || x < 0 || y < 0)) {
+      const size_t gi = plane + (size_t)y * W + x;
+      dl = dL_dmap[gi]; m1 = dm_dmu1[gi]; m2 = dm_dsigma1_sq[gi]; m3 = dm_dsigma12[gi];
+    }
+    t1[ly][lx] = m1 * dl;
+    t2[ly][lx] = m2 * dl;
+    t3[ly][lx] = m3 * dl;
+  }
+  __syncthreads();
+  for (int t = tid; t < SS_SY * SS_BX; t += SS_THREADS) {
+    const int ly = t / SS_BX, lx = t % SS_BX;
+    float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float g = SS_G[k];
+      a += g * t1[ly][lx + k];
+      b += g * t2[ly][lx + k];
+      c += g * t3[ly][lx + k];
+    }
+    xc[0][ly][lx] = a; xc[1][ly][lx] = b; xc[2][ly][lx] = c;
+  }
+  __syncthreads();
+  const int lx = tid & 31;
+  const int px = blockIdx.x * SS_BX + lx;
+#pragma unroll
+  for (int r = 0; r < SS_BY / (SS_THREADS / 32); r++) {
+    const int ly = (tid >> 5) + r * (SS_THREADS / 32);
+    const int py = blockIdx.y * SS_BY + ly;
+    float q[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float val = 0.f;
+#pragma unroll
+      for (int k = 0; k < 11; k++) val += SS_G[k] * xc[c][ly + k][lx];
+      q[c] = val;
+    }
+    if (px < W && py < H) {
+      const size_t gi = plane + (size_t)py * W + px;
+      const float pix1 = img1[gi], pix2 = img2[gi];
+      float dL_dpix = 0.0f;
+      dL_dpix += q[0];
+      dL_dpix += pix1 * 2.0f * q[1];
+      dL_dpix += pix2 * q[2];
+      dL_dimg1[gi] = dL_dpix;
+    }
+  }
+}
+
+}  // namespace dogs
+
+using namespace dogs;
+
+extern "C" int fssim_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                             const float* img1, const float* img2, float* ssim_map, float* dm_dmu1,
+                             float* dm_dsigma1_sq, float* dm_dsigma12, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || CH <= 0 || H <= 0 || W <= 0) return 0;
+  if (!img1 || !img2 || !ssim_map) { set_error("fssim_forward: null pointer"); return 1; }
+  if ((dm_dmu1 == nullptr) != (dm_dsigma1_sq == nullptr) || (dm_dmu1 == nullptr) != (dm_dsigma12 == nullptr)) {
+    set_error("fssim_forward: pass all three derivative maps or none");
+    return 1;
+  }
+  if ((long long)B * CH > 65535) { set_error("fssim_forward: B*CH > 65535"); return 1; }
+  dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
+  fssim_fwd_kernel<<<grid, SS_THREADS, 0, s>>>(H, W, C1, C2, img1, img2, ssim_map, dm_dmu1,
+                                               dm_dsigma1_sq, dm_dsigma12);
+  return check_launch("fssim_forward", false, s);
+}
+
+extern "C" int fssim_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                              const float* img1, const float* img2, const float* dL_dmap,
+                              const float* dm_dmu1, const float* dm_dsigma1_sq,
+                              const float* dm_dsigma12, float* dL_dimg1, void* stream) {
+  (void)C1; (void)C2;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || CH <= 0 || H <= 0 || W <= 0) return 0;
+  if (!img1 || !img2 || !dL_dmap || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) {
+    set_error("fssim_backward: null pointer");
+    return 1;
+  }
+  if ((long long)B * CH > 65535) { set_error("fssim_backward: B*CH > 65535"); return 1; }
+  dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
+  fssim_bwd_kernel<<<grid, SS_THREADS, 0, s>>>(H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq,
+                                               dm_dsigma12, dL_dimg1);
+  return check_launch("fssim_backward", false, s);
+}

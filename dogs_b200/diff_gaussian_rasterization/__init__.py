@@ -1,0 +1,273 @@
+"""Drop-in for the reference's `diff_gaussian_rasterization` Python API
+(submodules/diff-gaussian-rasterization/diff_gaussian_rasterization/__init__.py): same
+`GaussianRasterizationSettings` fields, same `GaussianRasterizer.forward/markVisible/
+visible_filter` signatures and return values, same `SparseGaussianAdam.step(visibility, N)`,
+same validation errors — backed by the sm_100a kernels behind the C-ABI in include/dogs_b200.h.
+"""
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+
+class GaussianRasterizationSettings(NamedTuple):  # reference __init__.py:203-217
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool
+    depth_threshold: float
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    return tuple(i.cpu().clone() if isinstance(i, torch.Tensor) else i for i in input_tuple)
+
+
+def _params(rs, P, M, device):
+    f = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+    keep = (f(rs.bg), f(rs.viewmatrix), f(rs.projmatrix), f(rs.campos))
+    prm = L.DgrParams(
+        P=P, D=int(rs.sh_degree), M=M, W=int(rs.image_width), H=int(rs.image_height),
+        tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy),
+        scale_modifier=float(rs.scale_modifier), depth_threshold=float(rs.depth_threshold),
+        prefiltered=int(bool(rs.prefiltered)), antialiasing=int(bool(rs.antialiasing)),
+        debug=int(bool(rs.debug)),
+        bg=keep[0].data_ptr(), viewmatrix=keep[1].data_ptr(), projmatrix=keep[2].data_ptr(),
+        campos=keep[3].data_ptr())
+    return prm, keep
+
+
+def _c(t):
+    return t if t.numel() == 0 else L.require_cuda(t, "input")
+
+
+def rasterize_gaussians(means3D, means2D, dc, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, dc, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, dc, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.size(1) != 3:  # rasterize_points.cu:78-80
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        means3D, dc, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = map(
+            _c, (means3D, dc, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+        device = means3D.device
+        P = means3D.size(0)
+        # A fused [P,16,3] SH tensor without dc is accepted: split it.
+        if colors_precomp.numel() == 0 and dc.numel() == 0 and sh.numel() != 0:
+            dc, sh = sh[:, :1].contiguous(), sh[:, 1:].contiguous()
+        M = sh.size(1) if sh.numel() != 0 else 0
+        H, W = int(rs.image_height), int(rs.image_width)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        invdepth = torch.empty((1, H, W), dtype=torch.float32, device=device)
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        geom, binning, image, scratch = (L.Allocator(device) for _ in range(4))
+        num_rendered = 0
+        if P != 0:
+            prm, keep = _params(rs, P, M, device)
+            info = L.DgrForwardInfo()
+            with torch.cuda.device(device):
+                args = (C.byref(prm), L.ptr(means3D), L.ptr(dc), L.ptr(sh), L.ptr(colors_precomp),
+                        L.ptr(opacities), L.ptr(scales), L.ptr(rotations), L.ptr(cov3Ds_precomp),
+                        color.data_ptr(), invdepth.data_ptr(), radii.data_ptr(),
+                        geom.cb, None, binning.cb, None, image.cb, None, scratch.cb, None,
+                        C.byref(info), L.stream_ptr(device))
+                if rs.debug:  # reference __init__.py:92-104
+                    cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, colors_precomp, opacities, scales,
+                                                    rotations, cov3Ds_precomp, dc, sh))
+                    try:
+                        L.check(L.lib().dgr_forward(*args))
+                    except Exception as ex:
+                        torch.save(cpu_args, "snapshot_fw.dump")
+                        print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                        raise ex
+                else:
+                    L.check(L.lib().dgr_forward(*args))
+            num_rendered = info.num_rendered
+            del keep
+        else:
+            color.zero_(); invdepth.zero_()
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.M = M
+        empty = torch.empty(0, dtype=torch.uint8, device=device)
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, dc,
+                              sh, opacities, geom.last if geom.last is not None else empty,
+                              binning.last if binning.last is not None else empty,
+                              image.last if image.last is not None else empty)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, invdepth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _, grad_out_depth):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, dc, sh, opacities,
+         geomBuffer, binningBuffer, imgBuffer) = ctx.saved_tensors
+        device = means3D.device
+        P, M = means3D.size(0), ctx.M
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        use_sh = colors_precomp.numel() == 0
+        use_cov = cov3Ds_precomp.numel() != 0
+        grad_means3D, grad_means2D, grad_opacities = new(P, 3), new(P, 3), new(P, 1)
+        grad_dc = new(P, 1, 3) if use_sh else None
+        grad_sh = new(P, M, 3) if use_sh and M > 0 else None
+        grad_colors_precomp = None if use_sh else new(P, 3)
+        grad_scales = None if use_cov else new(P, 3)
+        grad_rotations = None if use_cov else new(P, 4)
+        grad_cov3Ds_precomp = new(P, 6) if use_cov else None
+        if P != 0:
+            prm, keep = _params(rs, P, M, device)
+            if grad_out_color is None:
+                grad_out_color = torch.zeros((3, prm.H, prm.W), dtype=torch.float32, device=device)
+            grad_out_color = grad_out_color.contiguous()
+            if grad_out_depth is not None:
+                grad_out_depth = grad_out_depth.contiguous()
+            scratch = L.Allocator(device)
+            with torch.cuda.device(device):
+                args = (C.byref(prm), ctx.num_rendered, L.ptr(means3D), L.ptr(dc), L.ptr(sh),
+                        L.ptr(colors_precomp), L.ptr(opacities), L.ptr(scales), L.ptr(rotations),
+                        L.ptr(cov3Ds_precomp), radii.data_ptr(), geomBuffer.data_ptr(),
+                        binningBuffer.data_ptr(), imgBuffer.data_ptr(), grad_out_color.data_ptr(),
+                        L.ptr(grad_out_depth), grad_means3D.data_ptr(), grad_means2D.data_ptr(),
+                        L.ptr(grad_dc), L.ptr(grad_sh), L.ptr(grad_colors_precomp),
+                        grad_opacities.data_ptr(), L.ptr(grad_scales), L.ptr(grad_rotations),
+                        L.ptr(grad_cov3Ds_precomp), scratch.cb, None, L.stream_ptr(device))
+                if rs.debug:  # reference __init__.py:153-166
+                    cpu_args = cpu_deep_copy_tuple((rs.bg, means3D, radii, colors_precomp, opacities,
+                                                    scales, rotations, cov3Ds_precomp, grad_out_color,
+                                                    dc, sh, grad_out_depth))
+                    try:
+                        L.check(L.lib().dgr_backward(*args))
+                    except Exception as ex:
+                        torch.save(cpu_args, "snapshot_bw.dump")
+                        print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                        raise ex
+                else:
+                    L.check(L.lib().dgr_backward(*args))
+            del keep
+        # depth_threshold scaling of grad_means2D (reference __init__.py:171-185) is fused into
+        # the preprocess-backward kernel.
+        return (grad_means3D, grad_means2D, grad_dc, grad_sh, grad_colors_precomp, grad_opacities,
+                grad_scales, grad_rotations, grad_cov3Ds_precomp, None)
+
+
+class GaussianRasterizer(nn.Module):  # reference __init__.py:220-300
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            positions = L.require_cuda(positions, "positions")
+            P = positions.size(0)
+            visible = torch.empty((P,), dtype=torch.bool, device=positions.device)
+            if P:
+                view = rs.viewmatrix.to(positions.device, torch.float32).contiguous()
+                proj = rs.projmatrix.to(positions.device, torch.float32).contiguous()
+                with torch.cuda.device(positions.device):
+                    L.check(L.lib().dgr_mark_visible(P, positions.data_ptr(), view.data_ptr(),
+                                                     proj.data_ptr(), visible.data_ptr(),
+                                                     L.stream_ptr(positions.device)))
+        return visible
+
+    def forward(self, means3D, means2D, opacities, dc=None, shs=None, colors_precomp=None,
+                scales=None, rotations=None, cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception(
+                'Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        if dc is None:
+            dc = torch.Tensor([])
+        if shs is None:
+            shs = torch.Tensor([])
+        if colors_precomp is None:
+            colors_precomp = torch.Tensor([])
+        if scales is None:
+            scales = torch.Tensor([])
+        if rotations is None:
+            rotations = torch.Tensor([])
+        if cov3D_precomp is None:
+            cov3D_precomp = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, dc, shs, colors_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, raster_settings)
+
+    def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        with torch.no_grad():
+            means3D = L.require_cuda(means3D, "means3D")
+            device = means3D.device
+            P = means3D.size(0)
+            radii = torch.empty((P,), dtype=torch.int32, device=device)
+            if P:
+                prm, keep = _params(rs, P, 0, device)
+                sc = None if scales is None else _c(scales)
+                ro = None if rotations is None else _c(rotations)
+                cv = None if cov3D_precomp is None else _c(cov3D_precomp)
+                with torch.cuda.device(device):
+                    L.check(L.lib().dgr_visible_filter(C.byref(prm), means3D.data_ptr(), L.ptr(sc),
+                                                       L.ptr(ro), L.ptr(cv), radii.data_ptr(),
+                                                       L.stream_ptr(device)))
+                del keep
+        return radii
+
+
+class SparseGaussianAdam(torch.optim.Adam):  # reference __init__.py:303-332
+    def __init__(self, params, lr, eps):
+        super().__init__(params=params, lr=lr, eps=eps)
+
+    @torch.no_grad()
+    def step(self, visibility, N):
+        for group in self.param_groups:
+            lr = group["lr"]
+            eps = group["eps"]
+            assert len(group["params"]) == 1, "more than one tensor in group"
+            param = group["params"][0]
+            if param.grad is None:
+                continue
+            state = self.state[param]
+            if len(state) == 0:
+                state['step'] = torch.tensor(0.0, dtype=torch.float32)
+                state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
+            exp_avg = state["exp_avg"]
+            exp_avg_sq = state["exp_avg_sq"]
+            M = param.numel() // N
+            adamUpdate(param, param.grad, exp_avg, exp_avg_sq, visibility, lr, 0.9, 0.999, eps, N, M)
+
+
+def adamUpdate(param, param_grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps, N, M):
+    """_C.adamUpdate (rasterize_points.cu:331-361): in-place sparse Adam step."""
+    for t in (param, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError("adamUpdate needs contiguous float32 CUDA tensors")
+    grad = param_grad.contiguous()
+    vis = visible.contiguous()
+    if vis.dtype != torch.bool:
+        raise RuntimeError("visibility must be a bool tensor")
+    if N * M == 0:
+        return
+    with torch.cuda.device(param.device):
+        L.check(L.lib().dgr_sparse_adam(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                                        exp_avg_sq.data_ptr(), vis.data_ptr(), float(lr), float(b1),
+                                        float(b2), float(eps), int(N), int(M),
+                                        L.stream_ptr(param.device)))

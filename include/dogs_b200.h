@@ -1,0 +1,170 @@
+/*
+ * dogs_b200.h — C-ABI of the B200-native (sm_100a) DOGS hot path.
+ *
+ * Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch
+ * types.  Every entry point returns 0 on success, non-zero on error;
+ * dogs_last_error() returns the message of the calling thread's last failure
+ * (the reference throws std::runtime_error / AT_ERROR instead:
+ * submodules/diff-gaussian-rasterization/rasterize_points.cu:78-80,
+ * cuda_rasterizer/rasterizer_impl.cu:382-385, cuda_rasterizer/auxiliary.h:177-184).
+ *
+ * All kernels are enqueued on the stream given by the caller (the reference uses
+ * the legacy default stream everywhere).  The library owns no device memory:
+ * persistent state and scratch come from caller-supplied allocation callbacks,
+ * exactly like the reference's std::function<char*(size_t)> resize callbacks
+ * (rasterize_points.cu:30-36,106-109; rasterizer_impl.cu:335-338).
+ */
+#ifndef DOGS_B200_H_INCLUDED
+#define DOGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOGS_B200_ABI_VERSION 1
+
+/* Allocation callback: must return a device pointer to >= bytes bytes, aligned to
+ * 256 B, valid until the caller decides to free it.  Mirrors resizeFunctional()
+ * (rasterize_points.cu:30-36). */
+typedef char* (*dogs_alloc_fn)(void* user, size_t bytes);
+
+/* ---- rasterizer ----------------------------------------------------------------
+ * Replaces CudaRasterizer::Rasterizer::{forward,backward,visible_filter,markVisible}
+ * (cuda_rasterizer/rasterizer.h:22-113) and the glue in rasterize_points.cu:54-252. */
+typedef struct DgrParams {
+  int32_t P;               /* number of Gaussians                                   */
+  int32_t D;               /* active SH degree 0..3  (raster_settings.sh_degree)    */
+  int32_t M;               /* SH "rest" coefficients per Gaussian = sh.size(1)      */
+  int32_t W, H;            /* image size                                            */
+  float tanfovx, tanfovy;
+  float scale_modifier;
+  float depth_threshold;   /* >0: grad_means2D *= min(1,(depth/thr)^2), __init__.py:171-185 */
+  int32_t prefiltered;
+  int32_t antialiasing;
+  int32_t debug;           /* !=0: synchronise + check after every launch (CHECK_CUDA) */
+  const float* bg;         /* [3]   device */
+  const float* viewmatrix; /* [16]  device, column-major (camera.py:131)            */
+  const float* projmatrix; /* [16]  device, column-major                            */
+  const float* campos;     /* [3]   device                                          */
+} DgrParams;
+
+/* Sizes / counters reported by dgr_forward (host side). */
+typedef struct DgrForwardInfo {
+  int32_t num_rendered;    /* tile instances that survive the per-tile cull (R_valid) */
+  int32_t num_visible;     /* Gaussians with radii > 0 and at least one instance (not synced: -1) */
+  size_t geom_bytes, binning_bytes, image_bytes, scratch_bytes;
+} DgrForwardInfo;
+
+/* Forward.  Nullable inputs follow the reference: exactly one of (dc+sh | colors_precomp),
+ * exactly one of (scales+rotations | cov3D_precomp).
+ *   out_color [3,H,W], out_invdepth [1,H,W], radii [P] are caller-allocated (need not be zeroed).
+ *   geom/binning/image callbacks allocate the state kept for backward; scratch may be freed
+ *   as soon as the call returns (stream-ordered). */
+int dgr_forward(const DgrParams* prm,
+                const float* means3D, const float* dc, const float* sh,
+                const float* colors_precomp, const float* opacities,
+                const float* scales, const float* rotations, const float* cov3D_precomp,
+                float* out_color, float* out_invdepth, int32_t* radii,
+                dogs_alloc_fn geom_alloc, void* geom_user,
+                dogs_alloc_fn binning_alloc, void* binning_user,
+                dogs_alloc_fn image_alloc, void* image_user,
+                dogs_alloc_fn scratch_alloc, void* scratch_user,
+                DgrForwardInfo* info, void* stream);
+
+/* Backward.  geom/binning/image are the buffers handed out during dgr_forward.
+ * Every gradient output is fully written (zeros where the reference relies on
+ * torch::zeros, rasterize_points.cu:196-207), so the caller may pass torch.empty.
+ * Nullable outputs: dL_ddc/dL_dsh (when colors_precomp was used), dL_dcolors_precomp,
+ * dL_dscales/dL_drotations (when cov3D_precomp was used), dL_dcov3D, dL_dinvdepth_in. */
+int dgr_backward(const DgrParams* prm, int32_t num_rendered,
+                 const float* means3D, const float* dc, const float* sh,
+                 const float* colors_precomp, const float* opacities,
+                 const float* scales, const float* rotations, const float* cov3D_precomp,
+                 const int32_t* radii,
+                 const char* geom, const char* binning, const char* image,
+                 const float* dL_dcolor, const float* dL_dinvdepth_in,
+                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_ddc, float* dL_dsh,
+                 float* dL_dcolors_precomp, float* dL_dopacity,
+                 float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
+
+/* rasterize_gaussians_filter (rasterize_points.cu:274-329): radii only, no +0.3 low-pass. */
+int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* scales,
+                       const float* rotations, const float* cov3D_precomp,
+                       int32_t* radii, void* stream);
+/* mark_visible (rasterize_points.cu:254-272). present: [P] bytes (bool). */
+int dgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Introspection used by the parity tests (compare stage by stage with the reference's
+ * opaque buffers).  Offsets in bytes inside the geom / binning / image buffers. */
+typedef struct DgrLayout {
+  size_t geom_record;      /* float4[3*P]: {cx,cy,cz,o} {x,y,1/depth,r} {g,b,depth,-}   */
+  size_t geom_clamped;     /* uint8[P] bit c set => channel c clamped                  */
+  size_t geom_tiles;       /* uint32[P] instances after cull                           */
+  size_t geom_bytes;
+  size_t bin_point_list;   /* uint32[R] Gaussian id per sorted instance                */
+  size_t bin_tile_keys;    /* uint32[R] tile id per sorted instance                    */
+  size_t bin_bytes;
+  size_t img_ranges;       /* uint2[T]                                                 */
+  size_t img_final_T;      /* float[N]                                                 */
+  size_t img_n_contrib;    /* uint32[N]                                                */
+  size_t img_bytes;
+} DgrLayout;
+int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t num_rendered, DgrLayout* out);
+
+/* SparseGaussianAdam.step -> adamUpdate (cuda_rasterizer/adam.cu:9-66). visible: [N] bytes. */
+int dgr_sparse_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    const uint8_t* visible, float lr, float b1, float b2, float eps,
+                    uint32_t N, uint32_t M, void* stream);
+
+/* ---- fused-SSIM (submodules/fused-ssim/ssim.cu:368-444) ------------------------- */
+int fssim_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                  const float* img1, const float* img2, float* ssim_map,
+                  float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, /* NULL when !train */
+                  void* stream);
+int fssim_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                   const float* img1, const float* img2, const float* dL_dmap,
+                   const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                   float* dL_dimg1, void* stream);
+
+/* ---- simple-knn distCUDA2 (submodules/simple-knn/spatial.cu:17-35) --------------- */
+int sknn_dist2(int32_t P, const float* points, float* mean_dist2,
+               dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
+
+/* ---- ADMM consensus (conerf/trainers/{slave,master}_gaussian_trainer.py) --------
+ * A Gaussian has 59 parameters in 6 groups (xyz 3, f_dc 3, f_rest 45, scaling 3,
+ * quaternion 4, opacity 1); the 6 tensors stay separate (the model's own layout).  */
+#define ADMM_GROUPS 6
+typedef struct AdmmTensors { float* g[ADMM_GROUPS]; } AdmmTensors;
+typedef struct AdmmConstTensors { const float* g[ADMM_GROUPS]; } AdmmConstTensors;
+
+/* pack: sendbuf[slot[i]*59 + :] = x[local_idx[i]] for the S shared Gaussians of this block;
+ * zero_fill != 0 first clears the whole [S_total,59] buffer (rows owned by other blocks stay 0). */
+int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, const int64_t* slot,
+              int64_t S, int64_t S_total, int32_t zero_fill, float* sendbuf, void* stream);
+/* unpack_update after the all-reduce(sum), over ALL n Gaussians of the block.
+ * slot_of_local[i] >= 0 (shared): z = recv[slot]*inv_count[i]; u += relax*(x - z);
+ * slot_of_local[i] <  0 (owned by this block only): z = x, u untouched (master:551-555 with count 1).
+ * residuals (device double[12]) is ACCUMULATED: [0..5] sum((z-x)^2) per group (primal, master:396-432),
+ * [6..11] sum(inv_count*(z_prev-z)^2) per group (dual, master:435-456; each global Gaussian once). */
+int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
+                       const int64_t* slot_of_local, const float* inv_count, int64_t n,
+                       const float* recvbuf, float relax, double* residuals, void* stream);
+/* penalty (slave:161-202): sums[g] += sum((x_g+u_g-z_g)^2) (device double[6]); if grad != NULL,
+ * grad_g += coef[g]*(x_g+u_g-z_g) with coef[g] = rho_g/numel_g (host float[6]) — the gradient of
+ * 0.5*rho_g*mse_loss(x_g+u_g, z_g). */
+int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u, const AdmmConstTensors* z,
+                 const AdmmTensors* grad, int64_t n, const float* coef /* host[6] */,
+                 double* sums /* device[6] */, void* stream);
+
+const char* dogs_last_error(void);
+int dogs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+#!/usr/bin/env bash
+# Test infrastructure, NOT product code.
+#
+# Compiles the UNMODIFIED reference CUDA extensions (diff-gaussian-rasterization,
+# fused-ssim, simple-knn) for sm_100a straight from the read-only sources under
+# $REF (default /root/reference) into oracle/_ref/ (git-ignored, travels to the
+# GPU box with gpurun).  Only build OUTPUTS land in oracle/_ref: shared objects
+# and the reference's two tiny Python front-ends, copied at build time so the
+# reference is driven through its own public API.  No reference source is
+# committed to this repository.
+#
+# Numeric contract: nvcc 12.9 default flags (no -use_fast_math, -fmad default)
+# plus the two include fixes recorded in SURVEY.md 8(c):
+#   -include cstdint  (cuda_rasterizer/rasterizer_impl.h uses std::uintptr_t)
+#   -include cfloat   (simple_knn.cu uses FLT_MAX)
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+OBJ="$OUT/obj"
+PY=${PYTHON:-python}
+[ -d "$REF/submodules" ] || { echo "reference not present at $REF: nothing to build"; exit 0; }
+mkdir -p "$OBJ" "$OUT/diff_gaussian_rasterization" "$OUT/fused_ssim" "$OUT/simple_knn"
+
+read -r -a TINC <<<"$($PY - <<'PY'
+from torch.utils.cpp_extension import include_paths
+import sysconfig
+print(" ".join("-I"+p for p in include_paths("cuda")+[sysconfig.get_paths()["include"]]))
+PY
+)"
+TLIB="$($PY -c 'import torch,os;print(os.path.join(os.path.dirname(torch.__file__),"lib"))')"
+ABI="$($PY -c 'import torch;print(int(torch._C._GLIBCXX_USE_CXX11_ABI))')"
+COMMON=(-D__CUDA_NO_HALF_OPERATORS__ -D__CUDA_NO_HALF_CONVERSIONS__ -D__CUDA_NO_BFLOAT16_CONVERSIONS__
+        -D__CUDA_NO_HALF2_OPERATORS__ --expt-relaxed-constexpr -std=c++17
+        -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -w
+        -DTORCH_API_INCLUDE_EXTENSION_H -D_GLIBCXX_USE_CXX11_ABI=$ABI "${TINC[@]}")
+DGR="$REF/submodules/diff-gaussian-rasterization"
+SSIM="$REF/submodules/fused-ssim"
+KNN="$REF/submodules/simple-knn"
+
+cc() { # cc <obj> <src> <extname> [extra...]
+  local o="$1" s="$2" n="$3"; shift 3
+  if [ "$o" -nt "$s" ]; then return 0; fi
+  nvcc "${COMMON[@]}" -DTORCH_EXTENSION_NAME="$n" "$@" -c "$s" -o "$o"
+}
+pids=()
+cc "$OBJ/dgr_impl.o"    "$DGR/cuda_rasterizer/rasterizer_impl.cu" _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_fwd.o"     "$DGR/cuda_rasterizer/forward.cu"         _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_bwd.o"     "$DGR/cuda_rasterizer/backward.cu"        _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_adam.o"    "$DGR/cuda_rasterizer/adam.cu"            _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_points.o"  "$DGR/rasterize_points.cu"                _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_conv.o"    "$DGR/conv.cu"                            _C -I"$DGR/third_party/glm" -include cstdint & pids+=($!)
+cc "$OBJ/dgr_ext.o"     "$DGR/ext.cpp"                            _C -I"$DGR/third_party/glm" -include cstdint -x cu & pids+=($!)
+cc "$OBJ/ssim.o"        "$SSIM/ssim.cu"       fused_ssim_cuda & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+pids=()
+cc "$OBJ/ssim_ext.o"    "$SSIM/ext.cpp"       fused_ssim_cuda -x cu & pids+=($!)
+cc "$OBJ/knn.o"         "$KNN/simple_knn.cu"  _C -include cfloat & pids+=($!)
+cc "$OBJ/knn_spatial.o" "$KNN/spatial.cu"     _C -include cfloat & pids+=($!)
+cc "$OBJ/knn_ext.o"     "$KNN/ext.cpp"        _C -x cu & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+
+LINK=(-shared -L"$TLIB" -lc10 -lc10_cuda -ltorch_cpu -ltorch_cuda -ltorch -ltorch_python
+      -L/usr/local/cuda/lib64 -lcudart -Xlinker -rpath -Xlinker "$TLIB")
+nvcc "${LINK[@]}" "$OBJ"/dgr_*.o -o "$OUT/diff_gaussian_rasterization/_C.so"
+nvcc "${LINK[@]}" "$OBJ"/ssim.o "$OBJ"/ssim_ext.o -o "$OUT/fused_ssim_cuda.so"
+nvcc "${LINK[@]}" "$OBJ"/knn.o "$OBJ"/knn_spatial.o "$OBJ"/knn_ext.o -o "$OUT/simple_knn/_C.so"
+# The reference's Python front-ends (build outputs, git-ignored): its own public API.
+cp "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"
+cp "$SSIM/fused_ssim/__init__.py" "$OUT/fused_ssim/__init__.py"
+: > "$OUT/simple_knn/__init__.py"
+echo "reference extensions built into $OUT"
