@@ -22,6 +22,7 @@ class DgrParams(C.Structure):
         ("prefiltered", C.c_int32), ("antialiasing", C.c_int32), ("debug", C.c_int32),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
         ("campos", C.c_void_p),
+        ("ref_bucket_cull_quirk", C.c_int32),
     ]
 
 

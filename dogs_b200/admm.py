@@ -1,0 +1,196 @@
+"""ADMM Gaussian consensus, one scene block per GPU (one process per GPU, torch.distributed/NCCL).
+
+Replaces the master/slave RPC round of the reference
+(conerf/trainers/master_gaussian_trainer.py:665-728, slave_gaussian_trainer.py:81-202):
+
+  reference (star RPC through rank 0)                     here (no master)
+  -----------------------------------------------------   -------------------------------------------
+  send_local_model: every block ships all 59 floats/G      pack: only Gaussians owned by >= 2 blocks are
+  to GPU0; z = scatter-add / count (master:538-555)        gathered into a dense [S_total,59] buffer
+  broadcast_global_gaussian_splat (master:523-535)         ONE all-reduce(sum) over NVLink on that buffer
+  update_dual_variables (slave:99-121)                     unpack_update kernel: z = sum/count, u += 1.5(x-z),
+  compute_primal/dual_residual (master:396-456)            partial residual sums in the same pass
+  adapt_penalty_parameters + set_penalty (master:337-393)  12-double all-reduce, identical rho update on every rank
+
+For a Gaussian owned by a single block the reference's average is z == x and u stays 0, so it needs
+no communication; the results are identical.
+
+The device kernels live in csrc/admm.cu (C-ABI: admm_pack / admm_unpack_update / admm_penalty).
+`ops` can be replaced by the tests to drive the host logic on CPU with the oracle; the default ops
+call the CUDA library and raise if it is missing.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+GROUP_SIZES = (3, 3, 45, 3, 4, 1)       # xyz, f_dc, f_rest, scaling(raw), quaternion(raw), opacity(raw)
+ROW = sum(GROUP_SIZES)                  # 59 floats = 236 B per Gaussian
+DEFAULT_ALPHAS = (1e5, 1e4, 1e5, 1e4, 1e5, 1e4)  # config/gaussian_splatting/urban3d_admm.yaml:45-50
+
+
+class ConsensusPlan:
+    """Static metadata of one block (rank): which local Gaussians are shared and where they live in
+    the dense exchange buffer.  Built once after the blocks are (re-)split
+    (select_gaussians_in_each_block, master:124-172)."""
+
+    def __init__(self, global_indices: torch.Tensor, count: torch.Tensor):
+        n_global = count.numel()
+        shared_global = count > 1
+        slot_of_global = torch.cumsum(shared_global.to(torch.int64), 0) - 1
+        self.n_global = int(n_global)
+        self.n_local = int(global_indices.numel())
+        self.S_total = int(shared_global.sum().item())
+        cnt_local = count[global_indices].to(torch.float32)
+        is_shared = shared_global[global_indices]
+        self.slot_of_local = torch.where(is_shared, slot_of_global[global_indices],
+                                         torch.full_like(global_indices, -1)).contiguous()
+        self.inv_count = (1.0 / cnt_local).contiguous()
+        self.local_idx = torch.nonzero(is_shared).squeeze(1).contiguous()
+        self.slot = self.slot_of_local[self.local_idx].contiguous()
+        self.S = int(self.local_idx.numel())
+
+    def to(self, device):
+        for k in ("slot_of_local", "inv_count", "local_idx", "slot"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+def build_plan(global_indices: torch.Tensor, n_global: int, group=None) -> ConsensusPlan:
+    """count[i] = number of blocks holding global Gaussian i (torch.bincount at master:168),
+    obtained with one all-reduce instead of on a master."""
+    count = torch.bincount(global_indices, minlength=n_global).to(torch.int32)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    return ConsensusPlan(global_indices, count)
+
+
+class CudaOps:
+    """The product path: sm_100a kernels behind the C-ABI."""
+
+    def __init__(self):
+        from . import _lib
+        self.L = _lib
+        self.lib = _lib.lib()      # raises if the library has not been built
+
+    def _t6(self, ts):
+        arr = self.L.AdmmTensors()
+        for i, t in enumerate(ts):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError("ADMM tensors must be contiguous float32 CUDA tensors")
+            arr.g[i] = t.data_ptr()
+        return arr
+
+    def pack(self, x, plan, sendbuf):
+        xs = self._t6(x)
+        dev = sendbuf.device
+        with torch.cuda.device(dev):
+            self.L.check(self.lib.admm_pack(C.byref(xs), plan.local_idx.data_ptr(), plan.slot.data_ptr(),
+                                            plan.S, plan.S_total, 1, sendbuf.data_ptr(),
+                                            self.L.stream_ptr(dev)))
+
+    def unpack_update(self, x, u, z, plan, recvbuf, relax, residuals):
+        xs, us, zs = self._t6(x), self._t6(u), self._t6(z)
+        dev = residuals.device
+        with torch.cuda.device(dev):
+            self.L.check(self.lib.admm_unpack_update(
+                C.byref(xs), C.byref(us), C.byref(zs), plan.slot_of_local.data_ptr(),
+                plan.inv_count.data_ptr(), plan.n_local, recvbuf.data_ptr() if recvbuf.numel() else None,
+                float(relax), residuals.data_ptr(), self.L.stream_ptr(dev)))
+
+    def penalty(self, x, u, z, grads, n, coef, sums):
+        xs, us, zs = self._t6(x), self._t6(u), self._t6(z)
+        gs = self._t6(grads) if grads is not None else None
+        carr = (C.c_float * 6)(*[float(c) for c in coef])
+        dev = sums.device
+        with torch.cuda.device(dev):
+            self.L.check(self.lib.admm_penalty(C.byref(xs), C.byref(us), C.byref(zs),
+                                               C.byref(gs) if gs is not None else None, n, carr,
+                                               sums.data_ptr(), self.L.stream_ptr(dev)))
+
+
+class AdmmBlock:
+    """ADMM state of one block: x (the model's raw parameter tensors, shared with the optimizer),
+    scaled duals u, local copy z of the consensus variables, penalties rho."""
+
+    def __init__(self, params: Sequence[torch.Tensor], plan: ConsensusPlan,
+                 alphas: Sequence[float] = DEFAULT_ALPHAS, over_relaxation_coeff: float = 0.5,
+                 mu: float = 10.0, tau_inc: float = 2.0, tau_dec: float = 2.0, group=None,
+                 ops=None):
+        assert len(params) == 6
+        self.x: List[torch.Tensor] = list(params)
+        n = plan.n_local
+        for t, sz in zip(self.x, GROUP_SIZES):
+            assert t.numel() == n * sz, "parameter tensor does not match the plan"
+        self.plan = plan
+        self.group = group
+        self.ops = ops if ops is not None else CudaOps()
+        dev = self.x[0].device
+        # setup_dual_variables (slave:81-97): u := 0;  z := x (set_global_gaussians after fusion)
+        self.u = [torch.zeros_like(t) for t in self.x]
+        self.z = [t.detach().clone() for t in self.x]
+        # setup_penalty_parameters (master:326-334): rho_g = alpha_g / N_global
+        self.rho = [a / plan.n_global for a in alphas]
+        self.relax = 1.0 + over_relaxation_coeff
+        self.mu, self.tau_inc, self.tau_dec = mu, tau_inc, tau_dec
+        self.buf = torch.zeros(max(plan.S_total, 1) * ROW, dtype=torch.float32, device=dev)
+        self.residuals = torch.zeros(12, dtype=torch.float64, device=dev)
+        self.pen_sums = torch.zeros(6, dtype=torch.float64, device=dev)
+        self.last_primal: Optional[List[float]] = None
+        self.last_dual: Optional[List[float]] = None
+
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    @torch.no_grad()
+    def consensus(self, adapt: bool = True):
+        """One consensus round: steps (2)-(6) of master_gaussian_trainer.train_iteration."""
+        x = [t.detach() for t in self.x]
+        self.ops.pack(x, self.plan, self.buf)
+        if self._world() > 1 and self.plan.S_total > 0:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        self.residuals.zero_()
+        self.ops.unpack_update(x, self.u, self.z, self.plan, self.buf, self.relax, self.residuals)
+        res = self.residuals.clone()
+        # primal_g = sum_k mse(z[idx_k], x_k): every block divides by its own element count
+        n = self.plan.n_local
+        for g, sz in enumerate(GROUP_SIZES):
+            res[g] /= max(n * sz, 1)
+        if self._world() > 1:
+            dist.all_reduce(res, op=dist.ReduceOp.SUM, group=self.group)
+        res = res.tolist()
+        primal = res[:6]
+        dual = [self.rho[g] * res[6 + g] / (self.plan.n_global * GROUP_SIZES[g]) for g in range(6)]
+        self.last_primal, self.last_dual = primal, dual
+        if adapt:  # adapt_penalty_parameters (master:337-377), evaluated identically on every rank
+            for g in range(6):
+                if primal[g] > self.mu * dual[g]:
+                    self.rho[g] *= self.tau_inc
+                elif dual[g] > self.mu * primal[g]:
+                    self.rho[g] /= self.tau_dec
+        return primal, dual
+
+    @torch.no_grad()
+    def add_penalty_grads_(self):
+        """add_admm_penalties (slave:161-202) fused with its own backward: accumulates
+        rho_g/numel_g * (x+u-z) into x.grad and returns the 6 penalty values as a device tensor
+        (no .item() host syncs, unlike slave:195-200)."""
+        n = self.plan.n_local
+        coef = [self.rho[g] / max(n * GROUP_SIZES[g], 1) for g in range(6)]
+        for t in self.x:
+            if t.grad is None:
+                t.grad = torch.zeros_like(t)
+        self.pen_sums.zero_()
+        self.ops.penalty([t.detach() for t in self.x], self.u, self.z, [t.grad for t in self.x], n, coef,
+                         self.pen_sums)
+        scale = torch.tensor([0.5 * c for c in coef], dtype=torch.float64, device=self.pen_sums.device)
+        return self.pen_sums * scale
+
+    def state_dict(self):
+        """What a checkpoint must persist for ADMM (slave:209-263 stores u_*, rho_*; the reference does
+        not persist z / indices)."""
+        return dict(u=self.u, z=self.z, rho=list(self.rho), slot_of_local=self.plan.slot_of_local,
+                    inv_count=self.plan.inv_count)

@@ -9,8 +9,10 @@ namespace dogs {
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr, float b1,
                                          float b2, float eps) {
-  m = b1 * m + (1.0f - b1) * g;
-  v = b2 * v + (1.0f - b2) * g * g;
+  // Explicit roundings = the FMA placement nvcc chose for the reference kernel (adam.cu:29-30 SASS):
+  // fma(g, 1-b1, b1*m) and fma(g, (1-b2)*g, b2*v); spelled out so inlining cannot change them.
+  m = __fmaf_rn(g, 1.0f - b1, __fmul_rn(b1, m));
+  v = __fmaf_rn(g, __fmul_rn(1.0f - b2, g), __fmul_rn(b2, v));
   float step = -lr * m / (sqrt(v) + eps);
   p += step;
 }

@@ -78,13 +78,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ pixel_colors, const float* __restrict__ pixel_invdepths,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_invdepths,
-                 float* __restrict__ accum) {
+                 float* __restrict__ accum, bool ref_quirk) {
   __shared__ float4 sA[2][TILE_PIX];
   __shared__ float4 sB[2][TILE_PIX];
   __shared__ float4 sC[2][TILE_PIX];
   __shared__ uint32_t sId[2][TILE_PIX];
   __shared__ float sAcc[TILE_PIX][11];
-  __shared__ uint32_t sMax;
+  __shared__ uint32_t sMax, sMaxRows01;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // warp w covers an 8x4 pixel block so that a splat's footprint hits few warps
@@ -115,7 +115,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
 
-  if (tid == 0) sMax = 0;
+  if (tid == 0) { sMax = 0; sMaxRows01 = 0; }
 #pragma unroll
   for (int k = 0; k < 11; k++) sAcc[tid][k] = 0.f;
   __syncthreads();
@@ -124,9 +124,17 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) atomicMax(&sMax, m);
+    // tile-local rows 0-1 (= the first warp of the reference's 16x16 forward block)
+    if (ref_quirk && warp < 2 && lane < 16) atomicMax(&sMaxRows01, last_contributor);
   }
   __syncthreads();
-  const uint32_t todo_total = min(range.y - range.x, sMax);  // backward.cu:505-507
+  if (ref_quirk) {
+    // Reference behaviour (see DgrParams::ref_bucket_cull_quirk): buckets of 32 entries whose first
+    // entry is >= max(n_contrib over rows 0-1) contribute nothing.
+    const uint32_t cut = (sMaxRows01 + 31u) & ~31u;
+    last_contributor = min(last_contributor, cut);
+  }
+  const uint32_t todo_total = min(range.y - range.x, ref_quirk ? min(sMax, (sMaxRows01 + 31u) & ~31u) : sMax);  // backward.cu:505-507
   const int rounds = (todo_total + TILE_PIX - 1) / TILE_PIX;
   const int my_slot = warp_reduce10_slot(lane);
 
@@ -574,7 +582,8 @@ int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b
   dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
   blend_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
                                              im.final_T, im.n_contrib, im.pix_color,
-                                             im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum);
+                                             im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
+                                             prm.ref_bucket_cull_quirk != 0);
   return check_launch("blend_bwd", prm.debug != 0, s);
 }
 

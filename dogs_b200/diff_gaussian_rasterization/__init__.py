@@ -5,12 +5,19 @@ visible_filter` signatures and return values, same `SparseGaussianAdam.step(visi
 same validation errors — backed by the sm_100a kernels behind the C-ABI in include/dogs_b200.h.
 """
 import ctypes as C
+import os
 from typing import NamedTuple
 
 import torch
 import torch.nn as nn
 
 from .. import _lib as L
+
+
+# False (default): exact gradients.  True: reproduce the reference's truncated backward (its
+# per-tile max_contrib only covers pixel rows 0-1 of each tile; see include/dogs_b200.h
+# DgrParams::ref_bucket_cull_quirk and DESIGN.md).  Also settable with DOGS_B200_REF_BWD_QUIRK=1.
+REFERENCE_BACKWARD_QUIRK = os.environ.get("DOGS_B200_REF_BWD_QUIRK", "0") == "1"
 
 
 class GaussianRasterizationSettings(NamedTuple):  # reference __init__.py:203-217
@@ -44,7 +51,7 @@ def _params(rs, P, M, device):
         prefiltered=int(bool(rs.prefiltered)), antialiasing=int(bool(rs.antialiasing)),
         debug=int(bool(rs.debug)),
         bg=keep[0].data_ptr(), viewmatrix=keep[1].data_ptr(), projmatrix=keep[2].data_ptr(),
-        campos=keep[3].data_ptr())
+        campos=keep[3].data_ptr(), ref_bucket_cull_quirk=int(bool(REFERENCE_BACKWARD_QUIRK)))
     return prm, keep
 
 

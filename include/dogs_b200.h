@@ -49,6 +49,11 @@ typedef struct DgrParams {
   const float* viewmatrix; /* [16]  device, column-major (camera.py:131)            */
   const float* projmatrix; /* [16]  device, column-major                            */
   const float* campos;     /* [3]   device                                          */
+  int32_t ref_bucket_cull_quirk; /* backward only.  0 (default): exact gradients.  1: reproduce the
+      reference's truncated backward: its per-tile max_contrib comes from cub::BlockReduce<uint32_t,256>
+      instantiated 1-D on a 16x16 block (forward.cu:495-500), which only reduces the tile's first
+      warp (pixel rows 0-1), so PerGaussianRenderCUDA (backward.cu:505-507) drops every 32-splat
+      bucket starting at or after max(n_contrib of rows 0-1).  See DESIGN.md "Reference defect". */
 } DgrParams;
 
 /* Sizes / counters reported by dgr_forward (host side). */

@@ -65,8 +65,12 @@ LINK=(-shared -L"$TLIB" -lc10 -lc10_cuda -ltorch_cpu -ltorch_cuda -ltorch -ltorc
 nvcc "${LINK[@]}" "$OBJ"/dgr_*.o -o "$OUT/diff_gaussian_rasterization/_C.so"
 nvcc "${LINK[@]}" "$OBJ"/ssim.o "$OBJ"/ssim_ext.o -o "$OUT/fused_ssim_cuda.so"
 nvcc "${LINK[@]}" "$OBJ"/knn.o "$OBJ"/knn_spatial.o "$OBJ"/knn_ext.o -o "$OUT/simple_knn/_C.so"
+# Field offsets of the reference's opaque state buffers, from its own fromChunk() carvers.
+nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -Xcompiler -fPIC -w -I"$DGR" -I"$DGR/third_party/glm" \
+     -include cstdint -shared "$HERE/ref_layout.cu" "$OBJ/dgr_impl.o" "$OBJ/dgr_fwd.o" "$OBJ/dgr_bwd.o" \
+     -o "$OUT/ref_layout.so" -lcudart
 # The reference's Python front-ends (build outputs, git-ignored): its own public API.
-cp "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"
-cp "$SSIM/fused_ssim/__init__.py" "$OUT/fused_ssim/__init__.py"
+install -m 644 "$DGR/diff_gaussian_rasterization/__init__.py" "$OUT/diff_gaussian_rasterization/__init__.py"
+install -m 644 "$SSIM/fused_ssim/__init__.py" "$OUT/fused_ssim/__init__.py"
 : > "$OUT/simple_knn/__init__.py"
 echo "reference extensions built into $OUT"

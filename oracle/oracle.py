@@ -1,0 +1,244 @@
+"""numpy front-end of the CPU oracle (oracle/dgr_oracle.c) plus numpy restatements of the ADMM
+consensus arithmetic.  TEST INFRASTRUCTURE ONLY — never imported by the product path.
+
+Parity status: the reference has no tests or golden vectors of its own; this oracle
+is pinned against tests/golden/*.npz, which were produced by running the unmodified reference
+CUDA build (oracle/_ref) on a B200 with tools/make_golden.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "dgr_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.orc_duplicate_keys.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def num_threads():
+    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+
+
+def preprocess(s, antialiasing=False):
+    """forward.cu:156-276.  s: scene dict of numpy arrays (see dogs_b200.scenes.make_scene)."""
+    P = s["means3D"].shape[0]
+    M = s["sh"].shape[1] if s.get("sh") is not None else 0
+    o = dict(radii=np.zeros(P, np.int32), means2D=np.zeros((P, 2), np.float32),
+             depths=np.zeros(P, np.float32), cov3D=np.zeros((P, 6), np.float32),
+             rgb=np.zeros((P, 3), np.float32), conic_opacity=np.zeros((P, 4), np.float32),
+             clamped=np.zeros((P, 3), np.uint8), tiles_touched=np.zeros(P, np.uint32))
+    lib().orc_preprocess(
+        C.c_int(P), C.c_int(int(s["sh_degree"])), C.c_int(M), _p(_f32(s["means3D"])),
+        _p(_f32(s.get("scales"))), C.c_float(s.get("scale_modifier", 1.0)),
+        _p(_f32(s.get("rotations"))), _p(_f32(s["opacities"])), _p(_f32(s.get("dc"))),
+        _p(_f32(s.get("sh"))), _p(_f32(s.get("cov3D_precomp"))), _p(_f32(s.get("colors_precomp"))),
+        _p(_f32(s["viewmatrix"])), _p(_f32(s["projmatrix"])), _p(_f32(s["campos"])),
+        C.c_int(int(s["W"])), C.c_int(int(s["H"])), C.c_float(s["tanfovx"]), C.c_float(s["tanfovy"]),
+        C.c_int(int(antialiasing)), _p(o["radii"]), _p(o["means2D"]), _p(o["depths"]), _p(o["cov3D"]),
+        _p(o["rgb"]), _p(o["conic_opacity"]), _p(o["clamped"]), _p(o["tiles_touched"]))
+    return o
+
+
+def binning(s, pre):
+    """rasterizer_impl.cu:120-220: keys (pads dropped), stable sort, tile ranges."""
+    P = pre["radii"].shape[0]
+    W, H = int(s["W"]), int(s["H"])
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    cap = int(pre["tiles_touched"].sum())
+    keys = np.zeros(max(cap, 1), np.uint64)
+    vals = np.zeros(max(cap, 1), np.uint32)
+    counts = np.zeros(P, np.uint32)
+    n = lib().orc_duplicate_keys(C.c_int(P), _p(pre["means2D"]), _p(pre["conic_opacity"]),
+                                 _p(pre["depths"]), _p(pre["radii"]), C.c_int(W), C.c_int(H),
+                                 _p(keys), _p(vals), _p(counts))
+    keys, vals = keys[:n].copy(), vals[:n].copy()
+    unsorted_keys = keys.copy()
+    lib().orc_sort_pairs(C.c_int64(n), _p(keys), _p(vals))
+    ranges = np.zeros((T, 2), np.uint32)
+    lib().orc_tile_ranges(C.c_int64(n), _p(keys), C.c_int(T), _p(ranges))
+    return dict(keys=keys, point_list=vals, ranges=ranges, counts=counts, keys_unsorted=unsorted_keys)
+
+
+def render_fwd(s, pre, bins, bg=None):
+    """forward.cu:349-501."""
+    W, H = int(s["W"]), int(s["H"])
+    bg = np.zeros(3, np.float32) if bg is None else _f32(bg)
+    o = dict(color=np.zeros((3, H, W), np.float32), invdepth=np.zeros((1, H, W), np.float32),
+             final_T=np.zeros(H * W, np.float32), n_contrib=np.zeros(H * W, np.uint32))
+    lib().orc_render_fwd(C.c_int(W), C.c_int(H), _p(bins["ranges"]), _p(bins["point_list"]),
+                         _p(pre["means2D"]), _p(pre["rgb"]), _p(pre["conic_opacity"]),
+                         _p(pre["depths"]), _p(bg), _p(o["color"]), _p(o["invdepth"]),
+                         _p(o["final_T"]), _p(o["n_contrib"]))
+    return o
+
+
+def forward(s, bg=None, antialiasing=False):
+    pre = preprocess(s, antialiasing)
+    bins = binning(s, pre)
+    img = render_fwd(s, pre, bins, bg)
+    return pre, bins, img
+
+
+def backward(s, pre, bins, img, dL_dcolor, dL_dinvdepth=None, bg=None, antialiasing=False,
+             depth_threshold=0.0, ref_quirk=False):
+    """backward.cu (render + cov2D + preprocess) -> dict of gradients shaped like the reference's."""
+    P = pre["radii"].shape[0]
+    W, H = int(s["W"]), int(s["H"])
+    M = s["sh"].shape[1]
+    bg = np.zeros(3, np.float32) if bg is None else _f32(bg)
+    acc = np.zeros((P, 10), np.float64)
+    dLc = _f32(dL_dcolor)
+    dLd = _f32(dL_dinvdepth)
+    lib().orc_render_bwd(C.c_int(W), C.c_int(H), _p(bins["ranges"]), _p(bins["point_list"]), _p(bg),
+                         _p(pre["means2D"]), _p(pre["conic_opacity"]), _p(pre["rgb"]),
+                         _p(pre["depths"]), _p(img["final_T"]), _p(img["n_contrib"]),
+                         _p(img["color"]), _p(img["invdepth"]), _p(dLc), _p(dLd), _p(acc),
+                         C.c_int(int(ref_quirk)))
+    g = dict(means3D=np.zeros((P, 3), np.float32), means2D=np.zeros((P, 3), np.float32),
+             dc=np.zeros((P, 1, 3), np.float32), sh=np.zeros((P, M, 3), np.float32),
+             colors=np.zeros((P, 3), np.float32), opacities=np.zeros((P, 1), np.float32),
+             scales=np.zeros((P, 3), np.float32), rotations=np.zeros((P, 4), np.float32),
+             cov3D=np.zeros((P, 6), np.float32))
+    lib().orc_preprocess_bwd(
+        C.c_int(P), C.c_int(int(s["sh_degree"])), C.c_int(M), _p(_f32(s["means3D"])), _p(pre["radii"]),
+        _p(_f32(s["dc"])), _p(_f32(s["sh"])), _p(pre["clamped"]), _p(_f32(s["opacities"])),
+        _p(_f32(s["scales"])), _p(_f32(s["rotations"])), C.c_float(s.get("scale_modifier", 1.0)), None,
+        _p(_f32(s["viewmatrix"])), _p(_f32(s["projmatrix"])), C.c_int(W), C.c_int(H),
+        C.c_float(s["tanfovx"]), C.c_float(s["tanfovy"]), _p(_f32(s["campos"])), _p(acc),
+        C.c_int(int(antialiasing)), C.c_float(depth_threshold), _p(g["means3D"]), _p(g["means2D"]),
+        _p(g["dc"]), _p(g["sh"]), _p(g["colors"]), _p(g["opacities"]), _p(g["scales"]),
+        _p(g["rotations"]), _p(g["cov3D"]))
+    return g
+
+
+def visible_filter(s):
+    P = s["means3D"].shape[0]
+    radii = np.zeros(P, np.int32)
+    lib().orc_visible_filter(C.c_int(P), _p(_f32(s["means3D"])), _p(_f32(s["scales"])),
+                             C.c_float(s.get("scale_modifier", 1.0)), _p(_f32(s["rotations"])), None,
+                             _p(_f32(s["viewmatrix"])), _p(_f32(s["projmatrix"])), C.c_int(int(s["W"])),
+                             C.c_int(int(s["H"])), C.c_float(s["tanfovx"]), C.c_float(s["tanfovy"]),
+                             _p(radii))
+    return radii
+
+
+def mark_visible(means, view):
+    P = means.shape[0]
+    out = np.zeros(P, np.uint8)
+    lib().orc_mark_visible(C.c_int(P), _p(_f32(means)), _p(_f32(view)), _p(out))
+    return out.astype(bool)
+
+
+def ssim_fwd(img1, img2, C1=0.01 ** 2, C2=0.03 ** 2, train=True):
+    a, b = _f32(img1), _f32(img2)
+    B, CH, H, W = a.shape
+    m = np.zeros_like(a)
+    d = [np.zeros_like(a) for _ in range(3)] if train else [None] * 3
+    lib().orc_ssim_fwd(C.c_int(B * CH), C.c_int(H), C.c_int(W), C.c_float(C1), C.c_float(C2), _p(a),
+                       _p(b), _p(m), _p(d[0]), _p(d[1]), _p(d[2]))
+    return m, d[0], d[1], d[2]
+
+
+def ssim_bwd(img1, img2, dL_dmap, d1, d2, d3):
+    a, b, g = _f32(img1), _f32(img2), _f32(dL_dmap)
+    B, CH, H, W = a.shape
+    out = np.zeros_like(a)
+    lib().orc_ssim_bwd(C.c_int(B * CH), C.c_int(H), C.c_int(W), _p(a), _p(b), _p(g), _p(_f32(d1)),
+                       _p(_f32(d2)), _p(_f32(d3)), _p(out))
+    return out
+
+
+def knn_dist2(pts):
+    p = _f32(pts)
+    out = np.zeros(p.shape[0], np.float32)
+    lib().orc_knn_dist2(C.c_int(p.shape[0]), _p(p), _p(out))
+    return out
+
+
+def sparse_adam(param, grad, m, v, visible, lr, b1, b2, eps):
+    """In place on float32 arrays (adam.cu:9-38)."""
+    N = visible.shape[0]
+    M = param.size // N
+    vis = np.ascontiguousarray(visible, dtype=np.uint8)
+    lib().orc_sparse_adam(_p(param), _p(_f32(grad)), _p(m), _p(v), _p(vis), C.c_float(lr),
+                          C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_uint32(N), C.c_uint32(M))
+
+
+# ---- ADMM (numpy restatement of the reference's torch arithmetic) -------------------------------
+GROUPS = ("xyz", "fdc", "fr", "s", "q", "o")
+GROUP_SIZES = (3, 3, 45, 3, 4, 1)
+
+
+def admm_consensus(block_x, global_indices, n_global):
+    """master_gaussian_trainer.py:538-555 + gaussian_splat_model.py:316-340:
+    z = (sum_k scatter(x_k)) / count.  block_x: list over blocks of list of 6 arrays [n_k, size]."""
+    z = [np.zeros((n_global, sz), np.float32) for sz in GROUP_SIZES]
+    count = np.zeros(n_global, np.float32)
+    for xk, idx in zip(block_x, global_indices):
+        for g in range(6):
+            z[g][idx] += xk[g].reshape(len(idx), -1)       # plus_gaussians (indices unique per block)
+        count[idx] += 1
+    for g in range(6):
+        z[g] = (z[g] / count[:, None]).astype(np.float32)   # average_gaussians
+    return z, count
+
+
+def admm_dual_update(x, u, z_local, relax=1.5):
+    """slave_gaussian_trainer.py:99-121: u += (1 + alpha) * (x - z)."""
+    return [(ug + np.float32(relax) * (xg - zg)).astype(np.float32) for xg, ug, zg in zip(x, u, z_local)]
+
+
+def admm_penalty(x, u, z_local, rho):
+    """slave_gaussian_trainer.py:161-202: sum_g 0.5*rho_g*mse(x_g+u_g, z_g) and its gradient."""
+    pens, grads = [], []
+    for g in range(6):
+        r = (x[g] + u[g]) - z_local[g]
+        pens.append(0.5 * rho[g] * float(np.mean(r.astype(np.float64) ** 2)))
+        grads.append((rho[g] / r.size * r).astype(np.float32))
+    return pens, grads
+
+
+def admm_residuals(block_x, global_indices, z, z_prev, rho):
+    """master:396-456: primal_g = sum_k mse(z[idx_k], x_k); dual_g = rho_g * mse(z_prev, z)."""
+    primal = [0.0] * 6
+    for xk, idx in zip(block_x, global_indices):
+        for g in range(6):
+            d = z[g][idx].astype(np.float64) - xk[g].reshape(len(idx), -1)
+            primal[g] += float(np.mean(d ** 2))
+    dual = [rho[g] * float(np.mean((z_prev[g].astype(np.float64) - z[g]) ** 2)) for g in range(6)]
+    return primal, dual
+
+
+def admm_adapt(rho, primal, dual, mu=10.0, tau_inc=2.0, tau_dec=2.0):
+    """master:337-377."""
+    out = list(rho)
+    for g in range(6):
+        if primal[g] > mu * dual[g]:
+            out[g] *= tau_inc
+        elif dual[g] > mu * primal[g]:
+            out[g] /= tau_dec
+    return out
