@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DOGS rasterizer hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--cfg C3]
+
+Metric (BASELINE.json): 3DGS forward+backward iterations/s at 1080p with 3 M Gaussians.
+A step = rasterizer forward + loss (0.8*L1 + 0.2*(1 - fused_ssim), gaussian_trainer.py:403-405)
++ backward to every Gaussian parameter, on a seeded synthetic C3 scene.
+
+  value  device-timed (CUDA events) whole-job iterations/s with scene, camera and target resident in HBM.
+  e2e    same step through the public drop-in API with the per-step HOST inputs of a training
+         iteration (camera matrices + target image, pinned) copied H2D and the loss read back D2H
+         inside the timed region (gaussian_trainer.py:338-359, :415-427).  The Gaussians are model
+         state and stay resident, as in the reference.
+  N > 1  one process per GPU, one scene block per rank (ADMM block training): the same
+         step plus the ADMM penalty gradients every iteration and ONE consensus round (pack ->
+         NCCL all-reduce of the shared-Gaussian buffer -> unpack/dual update) per timed region.
+         Weak scaling: value = all ranks' iterations / max-over-ranks time.
+  --impl reference   the UNMODIFIED reference CUDA extensions (oracle/_ref, built from
+         /root/reference by oracle/build_ref.sh) through their own public API, same workload.
+         Its cpu_baseline field is the CPU oracle port timed on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "3dgs_fwd_bwd_iters_per_s_1080p_3M"
+UNIT = "iters/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:  # pylint: disable=W0703
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def load_modules(impl):
+    if impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refutil
+        if not refutil.ref_available():
+            return None
+        dgr, ssim, _ = refutil.ref_modules()
+        return dgr, ssim.fused_ssim
+    import dogs_b200.diff_gaussian_rasterization as dgr
+    from dogs_b200.fused_ssim import fused_ssim
+    return dgr, fused_ssim
+
+
+def cpu_baseline(scene_cpu, n_tiles_sample=48, seed=0):
+    """CPU oracle (kind 'port') on a bounded sample of the same workload: preprocess + binning of
+    ALL Gaussians, blend forward + backward on a random subset of tiles scaled to the full image,
+    preprocess backward on all Gaussians.  One thread (the port is scalar C)."""
+    import numpy as np
+    from oracle import oracle as O
+    s = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in scene_cpu.items()}
+    W, H = int(s["W"]), int(s["H"])
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    rng = np.random.default_rng(seed)
+    sel = np.zeros(T, np.uint8)
+    sel[rng.choice(T, size=min(n_tiles_sample, T), replace=False)] = 1
+    t0 = time.perf_counter()
+    pre = O.preprocess(s)
+    bins = O.binning(s, pre)
+    t1 = time.perf_counter()
+    img = O.render_fwd(s, pre, bins, tile_sel=sel)
+    dL = rng.standard_normal((3, H, W)).astype(np.float32) / (3 * H * W)
+    t2 = time.perf_counter()
+    O.backward(s, pre, bins, img, dL, None, tile_sel=sel)   # includes preprocess backward over all P
+    t3 = time.perf_counter()
+    # split backward: the tile part scales, the per-Gaussian part does not; estimate the latter as ~ preprocess time
+    per_gauss = (t1 - t0)
+    tile_fwd = (t2 - t1)
+    tile_bwd = max((t3 - t2) - per_gauss, 0.0)
+    scale = T / float(sel.sum())
+    total = 2 * per_gauss + scale * (tile_fwd + tile_bwd)
+    return {"value": 1.0 / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"all {s['means3D'].shape[0]} Gaussians preprocessed+binned+preprocess-bwd, blend fwd+bwd on "
+                      f"{int(sel.sum())} of {T} tiles scaled x{scale:.1f}; {t3 - t0:.1f} s of CPU work",
+            "est_s_per_iter": total}
+
+
+def make_block(cfg, rank, dev):
+    from dogs_b200 import scenes
+    sc = scenes.make_scene(cfg, seed=rank, device=dev)
+    torch.manual_seed(1234 + rank)
+    target = torch.rand(3, sc["H"], sc["W"], device=dev)
+    return sc, target
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                    # rank 0 alone runs the reference arm
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device (the hot path has no CPU fallback)"}))
+        return 0
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    distributed = world > 1 and args.impl == "ours"
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    mods = load_modules(args.impl)
+    if mods is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)"}))
+        return 0
+    dgr, fused_ssim = mods
+    from dogs_b200 import scenes
+    sc, target = make_block(args.cfg, rank, dev)
+    P, H, Wd = sc["means3D"].shape[0], sc["H"], sc["W"]
+    names = ("means3D", "dc", "sh", "opacities", "scales", "rotations")
+    params = {k: sc[k].clone().requires_grad_(True) for k in names}
+
+    admm = None
+    if distributed:
+        # ADMM block state: 1-D chain of blocks, 24.5 % of a block shared with each neighbour (~49 % shared,
+        # SURVEY.md 8d C4/C5).  The consensus variables are the 6 parameter tensors of the block.
+        from dogs_b200 import admm as A
+        ov = int(0.245 * P)
+        stride = P - ov
+        gidx = torch.arange(P, dtype=torch.int64) + rank * stride
+        n_global = stride * (world - 1) + P
+        plan = A.build_plan(gidx.to(dev), n_global).to(dev)
+        x = [params["means3D"], params["dc"].view(P, 3), params["sh"].view(P, 45), params["scales"],
+             params["rotations"], params["opacities"]]
+        admm = A.AdmmBlock([t.detach() for t in x], plan)
+        admm.x = x                                   # penalty gradients accumulate into the live .grad
+
+    def loss_of(img, tgt):
+        l1 = (img - tgt).abs().mean()
+        return 0.8 * l1 + 0.2 * (1.0 - fused_ssim(img[None], tgt[None]))
+
+    def step(scene, tgt):
+        for v in params.values():
+            v.grad = None
+        img, radii, depth, spts = scenes.render(dgr, scene, params)
+        loss = loss_of(img, tgt)
+        loss.backward()
+        if admm is not None:
+            admm.add_penalty_grads_()
+        return loss
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = None
+    if args.impl == "ours":
+        from dogs_b200 import _lib
+        lib = _lib.lib()
+
+    for _ in range(Wm):
+        step(sc, target)
+    if admm is not None:
+        admm.consensus()
+    barrier()
+
+    # ---- value: inputs resident in HBM, device-timed --------------------------------------------
+    n0 = lib.dogs_launch_count() if lib else 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            step(sc, target)
+        if admm is not None:
+            admm.consensus()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = (lib.dogs_launch_count() - n0) if lib else 0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * K / (ms_total / 1e3) if args.impl == "ours" else K / (ms_total / 1e3)
+
+    # ---- e2e: host inputs of a training iteration H2D, loss D2H, every step -------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_target = torch.empty(3, H, Wd, dtype=torch.float32).pin_memory()
+        host_target.copy_(target.cpu())
+        host_cam = {k: sc[k].cpu().pin_memory() for k in ("viewmatrix", "projmatrix", "campos")}
+        h2d = host_target.numel() * 4 + sum(v.numel() * 4 for v in host_cam.values())
+
+        def e2e_step():
+            scene = dict(sc)
+            for k, v in host_cam.items():
+                scene[k] = v.to(dev, non_blocking=True)
+            tgt = host_target.to(dev, non_blocking=True)
+            return float(step(scene, tgt).item())   # .item(): D2H read of the loss (4 B)
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            e2e_step()
+        if admm is not None:
+            admm.consensus()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nranks = world if args.impl == "ours" else 1
+        e2e = {"value": nranks * K / (float(t.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel (blend backward), timed live with CUDA events ---------------
+    roofline = None
+    stats = {}
+    if args.impl == "ours" and rank == 0:
+        roofline, stats = blend_bwd_roofline(sc, params, dev)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world if args.impl == "ours" else 1,
+            "steps": K, "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.cfg}: {P} Gaussians/block, {Wd}x{H}, SH degree 3, rasterize fwd + "
+                                   f"0.8*L1+0.2*(1-SSIM) + bwd" + (", ADMM penalty/iter + 1 consensus round per "
+                                   f"{K} iters, one block per GPU" if distributed else ""),
+                       "l2_policy": "inputs (708 MB of Gaussian parameters + 10 M instance lists) exceed the 126 MB L2",
+                       "blocks": world if args.impl == "ours" else 1},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+        }
+        if args.impl == "reference":
+            out["impl"] = "reference"
+            out["reference_kind"] = "unmodified reference CUDA extensions (oracle/_ref) on the same GPU"
+        if e2e is not None:
+            out["e2e"] = e2e
+        if roofline is not None:
+            out["roofline"] = roofline
+            out["scene_stats"] = stats
+        if not args.no_cpu_baseline and world == 1 or (args.impl == "reference" and not args.no_cpu_baseline):
+            try:
+                sc_cpu = scenes.make_scene(args.cfg, seed=0, device="cpu")
+                out["cpu_baseline"] = cpu_baseline(sc_cpu)
+            except Exception as ex:  # pylint: disable=W0703
+                out["cpu_baseline"] = {"error": str(ex)}
+        print(json.dumps(out), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def blend_bwd_roofline(sc, params, dev, reps=10):
+    """Times blend_bwd_kernel alone (CUDA events on the launching stream) through the C-ABI's
+    dgr_backward minus preprocess_bwd is not separable from outside, so the kernel pair is timed with
+    the library's own stage timer (dgr_backward on a prepared forward state).  Bound: FP32 issue
+    (no stage is a dense contraction); reported against the measured HBM peak as the
+    contract asks, with the algorithmic bytes the kernel must move:
+      44 B per tile instance (4 B id + 40 B record) + 44 B per pixel (n_contrib, final_T, colour copy,
+      inverse depth, dL/dC, dL/dD) + 40 B per instance of gradient flush."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refutil as U
+    from dogs_b200 import _lib as L
+    o = U.ours_forward_raw(sc)
+    R = o["num_rendered"]
+    H, Wd = sc["H"], sc["W"]
+    N = H * Wd
+    sum_nc = int(o["n_contrib"].long().sum().item())
+    stats = {"num_rendered": int(R), "visible": int((o["radii"] > 0).sum().item()),
+             "sum_n_contrib": sum_nc, "pixels": N}
+    al, keep = o["_keep"]
+    from dogs_b200.diff_gaussian_rasterization import _params, GaussianRasterizationSettings
+    P = sc["means3D"].shape[0]
+    bg = torch.zeros(3, device=dev)
+    rs = GaussianRasterizationSettings(H, Wd, sc["tanfovx"], sc["tanfovy"], bg, 1.0, sc["viewmatrix"],
+                                       sc["projmatrix"], 3, sc["campos"], False, False, False, 0.0)
+    prm, keep2 = _params(rs, P, 15, dev)
+    dLc = torch.randn(3, H, Wd, device=dev) / N
+    new = lambda *s: torch.empty(s, device=dev)
+    outs = [new(P, 3), new(P, 3), new(P, 3), new(P, 45), None, new(P, 1), new(P, 3), new(P, 4), None]
+    scratch = L.Allocator(dev)
+    times = L.lib().dgr_backward_timed
+    times.restype = C.c_int
+    stage = (C.c_float * 2)()
+    best = [1e30, 1e30]
+    for _ in range(reps):
+        L.check(times(C.byref(prm), R, sc["means3D"].data_ptr(), sc["dc"].data_ptr(), sc["sh"].data_ptr(), None,
+                      sc["opacities"].data_ptr(), sc["scales"].data_ptr(), sc["rotations"].data_ptr(), None,
+                      o["radii"].data_ptr(), al[0].last.data_ptr(), al[1].last.data_ptr(), al[2].last.data_ptr(),
+                      dLc.data_ptr(), None, *[L.ptr(t) for t in outs], scratch.cb, None,
+                      L.stream_ptr(dev), stage))
+        best = [min(best[0], stage[0]), min(best[1], stage[1])]
+        scratch.buffers.clear()
+    peak, how = peaks()
+    alg_bytes = 44.0 * R + 44.0 * N + 40.0 * R
+    achieved = alg_bytes / (best[0] * 1e-3) / 1e9
+    roof = {"kernel": "blend_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": how, "kernel_ms": best[0],
+            "algorithmic_bytes": alg_bytes,
+            "note": "the kernel is FP32-issue bound (no dense contraction): "
+                    f"{sum_nc} contributing (pixel,splat) pairs; preprocess_bwd_kernel {best[1]:.3f} ms"}
+    return roof, stats
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,6 +52,8 @@ SIGNATURES = {
                    + [C.POINTER(DgrForwardInfo), _P],
     "dgr_backward": [C.POINTER(DgrParams), C.c_int32] + [_P] * 8 + [_P] + [_P] * 3 + [_P, _P]
                     + [_P] * 9 + [ALLOC_FN, _P, _P],
+    "dgr_backward_timed": [C.POINTER(DgrParams), C.c_int32] + [_P] * 8 + [_P] + [_P] * 3 + [_P, _P]
+                          + [_P] * 9 + [ALLOC_FN, _P, _P, _P],
     "dgr_visible_filter": [C.POINTER(DgrParams), _P, _P, _P, _P, _P, _P],
     "dgr_mark_visible": [C.c_int32, _P, _P, _P, _P, _P],
     "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
@@ -65,6 +67,7 @@ SIGNATURES = {
     "admm_penalty": [C.POINTER(AdmmTensors)] * 3 + [_P, C.c_int64, _P, _P, _P],
     "dogs_last_error": [],
     "dogs_abi_version": [],
+    "dogs_launch_count": [],
 }
 
 _lib = None
@@ -84,6 +87,7 @@ def lib():
             fn.argtypes = args
             fn.restype = C.c_int
         _lib.dogs_last_error.restype = C.c_char_p
+        _lib.dogs_launch_count.restype = C.c_ulonglong
     return _lib
 
 

@@ -15,7 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int check_launch(const char* what, bool debug, cudaStream_t s) {
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return g_launches; }
+
+int check_launch(const char* what, bool debug, cudaStream_t s, int kernels) {
+  g_launches += (unsigned long long)kernels;
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && debug) e = cudaStreamSynchronize(s);  // CHECK_CUDA, auxiliary.h:177-184
   if (e != cudaSuccess) {
@@ -100,6 +104,7 @@ extern "C" {
 
 const char* dogs_last_error(void) { return g_err; }
 int dogs_abi_version(void) { return DOGS_B200_ABI_VERSION; }
+unsigned long long dogs_launch_count(void) { return dogs::launch_count(); }
 
 int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t R, DgrLayout* out) {
   if (!out) return 1;
@@ -226,14 +231,14 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
   return 0;
 }
 
-int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
+static int backward_impl(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
                  const float* sh, const float* colors_precomp, const float* opacities,
                  const float* scales, const float* rotations, const float* cov3D_precomp,
                  const int32_t* radii, const char* geom, const char* binning, const char* image,
                  const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
                  float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
-                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
+                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream, float* stage_ms) {
   cudaStream_t s = (cudaStream_t)stream;
   if (validate(prm)) return 1;
   const DgrParams& p = *prm;
@@ -248,13 +253,58 @@ int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3
   ImgState im = ImgState::carve(const_cast<char*>(image), N, T);
   float* accum = reinterpret_cast<float*>(scratch_alloc(scratch_user, bwd_accum_bytes(P)));
   if (!accum) { set_error("backward: scratch allocation failed"); return 1; }
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (stage_ms) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], s);
+  }
   if (launch_blend_bwd(p, g, b, im, dL_dcolor, dL_dinvdepth_in, accum, s)) return 1;
+  if (stage_ms) cudaEventRecord(ev[1], s);
   const bool sh_path = colors_precomp == nullptr;
-  return launch_preprocess_bwd(p, means3D, dc, sh, opacities, scales, rotations, cov3D_precomp, radii,
-                               g, accum, dL_dmeans3D, dL_dmeans2D, sh_path ? dL_ddc : nullptr,
-                               sh_path ? dL_dsh : nullptr, dL_dcolors_precomp, dL_dopacity,
-                               cov3D_precomp ? nullptr : dL_dscales,
-                               cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, s);
+  int rc = launch_preprocess_bwd(p, means3D, dc, sh, opacities, scales, rotations, cov3D_precomp, radii,
+                                 g, accum, dL_dmeans3D, dL_dmeans2D, sh_path ? dL_ddc : nullptr,
+                                 sh_path ? dL_dsh : nullptr, dL_dcolors_precomp, dL_dopacity,
+                                 cov3D_precomp ? nullptr : dL_dscales,
+                                 cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, s);
+  if (stage_ms) {
+    cudaEventRecord(ev[2], s);
+    cudaEventSynchronize(ev[2]);
+    cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&stage_ms[1], ev[1], ev[2]);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return rc;
+}
+
+int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
+                 const float* sh, const float* colors_precomp, const float* opacities,
+                 const float* scales, const float* rotations, const float* cov3D_precomp,
+                 const int32_t* radii, const char* geom, const char* binning, const char* image,
+                 const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
+                 float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
+                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
+  return backward_impl(prm, num_rendered, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
+                       cov3D_precomp, radii, geom, binning, image, dL_dcolor, dL_dinvdepth_in, dL_dmeans3D,
+                       dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
+                       dL_drotations, dL_dcov3D, scratch_alloc, scratch_user, stream, nullptr);
+}
+
+// dgr_backward + device time of its two stages (CUDA events on `stream`; synchronises):
+// stage_ms[0] = accumulator clear + blend_bwd_kernel, stage_ms[1] = preprocess_bwd_kernel.
+int dgr_backward_timed(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
+                       const float* sh, const float* colors_precomp, const float* opacities,
+                       const float* scales, const float* rotations, const float* cov3D_precomp,
+                       const int32_t* radii, const char* geom, const char* binning, const char* image,
+                       const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
+                       float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
+                       float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                       dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream, float* stage_ms) {
+  if (!stage_ms) { set_error("dgr_backward_timed: stage_ms is null"); return 1; }
+  return backward_impl(prm, num_rendered, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
+                       cov3D_precomp, radii, geom, binning, image, dL_dcolor, dL_dinvdepth_in, dL_dmeans3D,
+                       dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
+                       dL_drotations, dL_dcov3D, scratch_alloc, scratch_user, stream, stage_ms);
 }
 
 int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* scales,

@@ -13,7 +13,7 @@
 namespace dogs {
 
 void set_error(const char* fmt, ...);
-int check_launch(const char* what, bool debug, cudaStream_t s);
+int check_launch(const char* what, bool debug, cudaStream_t s, int kernels = 1);
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

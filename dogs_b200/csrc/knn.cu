@@ -128,7 +128,8 @@ knn_box_kernel(int P, const float4* __restrict__ sorted, KnnBox* __restrict__ bo
 
 __device__ __forceinline__ void update_k_best(const float3& ref, const float4& point, float* knn) {
   float3 d = {point.x - ref.x, point.y - ref.y, point.z - ref.z};
-  float dist = d.x * d.x + d.y * d.y + d.z * d.z;
+  // FMA placement of the reference's SASS (boxMeanDist): fma(dz,dz, fma(dx,dx, dy*dy))
+  float dist = __fmaf_rn(d.z, d.z, __fmaf_rn(d.x, d.x, __fmul_rn(d.y, d.y)));
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     if (knn[j] > dist) {
@@ -210,5 +211,5 @@ extern "C" int sknn_dist2(int32_t P, const float* points, float* mean_dist2,
   knn_gather_kernel<<<grid, 256, 0, s>>>(P, points, in_b ? ids_b : ids, sorted);
   knn_box_kernel<<<nboxes, KNN_BOX, 0, s>>>(P, sorted, boxes);
   knn_mean_dist_kernel<<<grid, 256, 0, s>>>(P, sorted, boxes, nboxes, mean_dist2);
-  return check_launch("sknn_dist2", false, s);
+  return check_launch("sknn_dist2", false, s, 6);
 }

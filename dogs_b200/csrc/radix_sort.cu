@@ -144,7 +144,10 @@ __global__ void iota_kernel(uint32_t* out, uint32_t n) {
   if (i < n) out[i] = i;
 }
 void launch_iota(uint32_t* out, size_t n, cudaStream_t s) {
-  if (n) iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, (uint32_t)n);
+  if (n) {
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, (uint32_t)n);
+    check_launch("iota", false, s);
+  }
 }
 
 size_t sort_pairs_scratch_bytes(size_t n) {
@@ -170,7 +173,7 @@ int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_
     radix_rowscan_kernel<<<RADIX, 256, 0, s>>>(hist, nblk, totals);
     radix_scatter_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, vi, ko, vo, (uint32_t)n, b, mask, hist,
                                                       nblk, totals);
-    if (int e = check_launch("radix pass", debug, s)) return e;
+    if (int e = check_launch("radix pass", debug, s, 3)) return e;
     uint32_t* t;
     t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
@@ -272,7 +275,7 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, u
   scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial);
   scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(partial, nb, total);
   scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial, out);
-  return check_launch("exclusive scan", debug, s);
+  return check_launch("exclusive scan", debug, s, 3);
 }
 
 }  // namespace dogs

@@ -83,7 +83,7 @@ def binning(s, pre):
     return dict(keys=keys, point_list=vals, ranges=ranges, counts=counts, keys_unsorted=unsorted_keys)
 
 
-def render_fwd(s, pre, bins, bg=None):
+def render_fwd(s, pre, bins, bg=None, tile_sel=None):
     """forward.cu:349-501."""
     W, H = int(s["W"]), int(s["H"])
     bg = np.zeros(3, np.float32) if bg is None else _f32(bg)
@@ -92,7 +92,7 @@ def render_fwd(s, pre, bins, bg=None):
     lib().orc_render_fwd(C.c_int(W), C.c_int(H), _p(bins["ranges"]), _p(bins["point_list"]),
                          _p(pre["means2D"]), _p(pre["rgb"]), _p(pre["conic_opacity"]),
                          _p(pre["depths"]), _p(bg), _p(o["color"]), _p(o["invdepth"]),
-                         _p(o["final_T"]), _p(o["n_contrib"]))
+                         _p(o["final_T"]), _p(o["n_contrib"]), _p(tile_sel))
     return o
 
 
@@ -104,7 +104,7 @@ def forward(s, bg=None, antialiasing=False):
 
 
 def backward(s, pre, bins, img, dL_dcolor, dL_dinvdepth=None, bg=None, antialiasing=False,
-             depth_threshold=0.0, ref_quirk=False):
+             depth_threshold=0.0, ref_quirk=False, tile_sel=None):
     """backward.cu (render + cov2D + preprocess) -> dict of gradients shaped like the reference's."""
     P = pre["radii"].shape[0]
     W, H = int(s["W"]), int(s["H"])
@@ -117,7 +117,7 @@ def backward(s, pre, bins, img, dL_dcolor, dL_dinvdepth=None, bg=None, antialias
                          _p(pre["means2D"]), _p(pre["conic_opacity"]), _p(pre["rgb"]),
                          _p(pre["depths"]), _p(img["final_T"]), _p(img["n_contrib"]),
                          _p(img["color"]), _p(img["invdepth"]), _p(dLc), _p(dLd), _p(acc),
-                         C.c_int(int(ref_quirk)))
+                         C.c_int(int(ref_quirk)), _p(tile_sel))
     g = dict(means3D=np.zeros((P, 3), np.float32), means2D=np.zeros((P, 3), np.float32),
              dc=np.zeros((P, 1, 3), np.float32), sh=np.zeros((P, M, 3), np.float32),
              colors=np.zeros((P, 3), np.float32), opacities=np.zeros((P, 1), np.float32),

@@ -37,7 +37,7 @@ for tile in [int(a) for a in sys.argv[1:]] or [4, 30, 17]:
     O.lib().orc_render_bwd(C.c_int(W), C.c_int(H), O._p(bins["ranges"]), O._p(bins["point_list"]), O._p(np.zeros(3, np.float32)),
                            O._p(pre["means2D"]), O._p(pre["conic_opacity"]), O._p(pre["rgb"]), O._p(pre["depths"]),
                            O._p(im["final_T"]), O._p(im["n_contrib"]), O._p(im["color"]), O._p(im["invdepth"]),
-                           O._p(np.ascontiguousarray(g.cpu().numpy())), None, O._p(accd))
+                           O._p(np.ascontiguousarray(g.cpu().numpy())), None, O._p(accd), C.c_int(0), None)
     lo, hi = bins["ranges"][tile]
     nc = im["n_contrib"].reshape(H, W)[ty * 16:ty * 16 + 16, tx * 16:tx * 16 + 16]
     print(f"tile {tile} len {hi-lo} n_contrib min {nc.min()} max {nc.max()}")
