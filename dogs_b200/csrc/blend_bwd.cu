@@ -1,0 +1,276 @@
+// blend_bwd_kernel — backward of the per-tile alpha blend (replaces PerGaussianRenderCUDA,
+// cuda_rasterizer/backward.cu:453-658).
+//
+// The reference walks each 32-splat bucket over the tile's 256 pixels and needs a (T, colour, depth)
+// snapshot per pixel per bucket from the forward pass (5 KB per bucket, ~1.6 GB at 3 M Gaussians).
+// Here every pixel replays its own front-to-back blend: T evolves bit-identically to the forward
+// pass and the entry count is bounded by n_contrib, so the forward stores no snapshot at all.
+//
+// Work layout (second version; ncu of the first version — one pixel per thread — showed the
+// kernel issue-bound with ~45 % of its instructions in the cross-lane reduction of the 10
+// gradient terms, profiles/r1_full_v1_kernels.md):
+//   * one CTA of 64 threads per 16x16 tile; each thread owns a 2x2 pixel quad, a warp a 16x8
+//     half tile.  The four pixels of a thread share the record loads and are summed in
+//     registers before anything crosses lanes, so the reduction runs once per (half tile, splat)
+//     instead of once per (32 pixels, splat);
+//   * the colour/depth prefix of the reference (ar[3], ard) is carried as ONE scalar
+//     S = sum_c ar_c * dL/dC_c + ard * dL/dD, which removes 3/4 of the per-pair state updates:
+//       dL/dalpha = T * (c . dL/dC + invd * dL/dD) + S / (1 - alpha)  - T_final * bg.dL/dC / (1 - alpha);
+//   * 10 totals reduced with a transposed butterfly (12 shuffles), accumulated per tile in shared
+//     memory, flushed with red.global.add.v4/v2.f32 (3 vector reductions per tile instance).
+#include "common.cuh"
+
+namespace dogs {
+
+constexpr int BB_THREADS = 64;   // 2 warps per tile
+constexpr int BB_BATCH = 64;     // records staged per round (one per thread)
+constexpr int BB_ACC = 12;       // floats per Gaussian in the global accumulator (3 x float4)
+
+__device__ __forceinline__ void bb_cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void bb_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void bb_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void bb_red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void bb_red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// Sum 10 per-lane values over the warp.  Afterwards lane l holds the total of value slot(l)
+// (see bb_slot); every total lives in two lanes (bit 0 of the lane id).
+__device__ __forceinline__ float bb_warp_reduce10(const float v[10], int lane) {
+  const unsigned full = 0xffffffffu;
+  bool hi = lane & 16;
+  float k[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    float keep = hi ? v[5 + i] : v[i];
+    float send = hi ? v[i] : v[5 + i];
+    k[i] = keep + __shfl_xor_sync(full, send, 16);
+  }
+  hi = lane & 8;
+  float a0 = (hi ? k[3] : k[0]) + __shfl_xor_sync(full, hi ? k[0] : k[3], 8);
+  float a1 = (hi ? k[4] : k[1]) + __shfl_xor_sync(full, hi ? k[1] : k[4], 8);
+  float a2 = (hi ? 0.f : k[2]) + __shfl_xor_sync(full, hi ? k[2] : 0.f, 8);
+  hi = lane & 4;
+  float b0 = (hi ? a2 : a0) + __shfl_xor_sync(full, hi ? a0 : a2, 4);
+  float b1 = (hi ? 0.f : a1) + __shfl_xor_sync(full, hi ? a1 : 0.f, 4);
+  hi = lane & 2;
+  float c = (hi ? b1 : b0) + __shfl_xor_sync(full, hi ? b0 : b1, 2);
+  c += __shfl_xor_sync(full, c, 1);
+  return c;
+}
+__device__ __forceinline__ int bb_slot(int lane) {
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+  if (lane & 1) return -1;
+  const int i2 = 2 * b2 + b1;
+  if (i2 > 2) return -1;
+  if (b3 && i2 > 1) return -1;
+  return 5 * b4 + 3 * b3 + i2;
+}
+
+// accumulator slots: 0 mean2D.x, 1 mean2D.y, 2 conic.x, 3 conic.y, 4 conic.w, 5 opacity,
+//                    6..8 colour rgb, 9 inverse depth
+__global__ void __launch_bounds__(BB_THREADS)
+blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
+                 int H, const float* __restrict__ bg_color, const SplatRecord* __restrict__ rec,
+                 const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                 const float* __restrict__ pixel_colors, const float* __restrict__ pixel_invdepths,
+                 const float* __restrict__ dL_dpixels, const float* __restrict__ dL_invdepths,
+                 float* __restrict__ accum, bool ref_quirk) {
+  __shared__ float4 sA[2][BB_BATCH];
+  __shared__ float4 sB[2][BB_BATCH];
+  __shared__ float4 sC[2][BB_BATCH];
+  __shared__ uint32_t sId[2][BB_BATCH];
+  __shared__ float sAcc[BB_BATCH][11];
+  __shared__ uint32_t sMax, sMaxRows01;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // thread -> 2x2 quad: warp w covers tile rows 8w..8w+7, lane (lx, ly) = (lane & 7, lane >> 3)
+  const uint32_t qx = blockIdx.x * TILE_X + 2 * (lane & 7);
+  const uint32_t qy = blockIdx.y * TILE_Y + 8 * warp + 2 * (lane >> 3);
+  const size_t HW = (size_t)H * W;
+  const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+  const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
+
+  // per-pixel state (k = 2*dy + dx)
+  uint32_t last[4];
+  float T[4], S[4], dC0[4], dC1[4], dC2[4], dD[4], bgT[4], pxf[4], pyf[4];
+  uint32_t lmax = 0, lmax01 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t px = qx + (k & 1), py = qy + (k >> 1);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    pxf[k] = (float)px;
+    pyf[k] = (float)py;
+    last[k] = 0; T[k] = 1.0f; S[k] = 0.f; dC0[k] = dC1[k] = dC2[k] = dD[k] = 0.f; bgT[k] = 0.f;
+    if (inside) {
+      const uint32_t pix_id = W * py + px;
+      last[k] = n_contrib[pix_id];
+      dC0[k] = dL_dpixels[0 * HW + pix_id];
+      dC1[k] = dL_dpixels[1 * HW + pix_id];
+      dC2[k] = dL_dpixels[2 * HW + pix_id];
+      dD[k] = dL_invdepths ? dL_invdepths[pix_id] : 0.f;
+      // S = sum_c (prefix_c - pixel_c) * dL/dC_c + (prefix_d - pixel_d) * dL/dD, prefix = 0 at the start
+      S[k] = -(pixel_colors[0 * HW + pix_id] * dC0[k] + pixel_colors[1 * HW + pix_id] * dC1[k] +
+               pixel_colors[2 * HW + pix_id] * dC2[k] + pixel_invdepths[pix_id] * dD[k]);
+      // backward.cu:604-621: the background term (-T_final/(1-alpha)) * (bg . dL/dC)
+      bgT[k] = final_Ts[pix_id] * (bg0 * dC0[k] + bg1 * dC1[k] + bg2 * dC2[k]);
+    }
+    lmax = max(lmax, last[k]);
+    // rows 0-1 of the tile = the first warp of the reference's 16x16 forward block
+    if (warp == 0 && (lane >> 3) == 0) lmax01 = max(lmax01, last[k]);
+  }
+  const float ddelx_dx = 0.5 * W;
+  const float ddely_dy = 0.5 * H;
+
+  if (tid == 0) { sMax = 0; sMaxRows01 = 0; }
+#pragma unroll
+  for (int k = 0; k < 11; k++) sAcc[tid][k] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    lmax01 = max(lmax01, __shfl_xor_sync(0xffffffffu, lmax01, o));
+  }
+  if (lane == 0) {
+    atomicMax(&sMax, lmax);
+    if (ref_quirk) atomicMax(&sMaxRows01, lmax01);
+  }
+  __syncthreads();
+  uint32_t todo_total = min(range.y - range.x, sMax);  // backward.cu:505-507 with the intended max
+  if (ref_quirk) {
+    // Reference behaviour (DgrParams::ref_bucket_cull_quirk): 32-entry buckets whose first entry is
+    // >= max(n_contrib over rows 0-1) contribute nothing.
+    const uint32_t cut = (sMaxRows01 + 31u) & ~31u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) last[k] = min(last[k], cut);
+    todo_total = min(todo_total, cut);
+  }
+  const int rounds = (todo_total + BB_BATCH - 1) / BB_BATCH;
+  const int my_slot = bb_slot(lane);
+
+  auto fetch = [&](int round, int buf) {
+    uint32_t progress = round * BB_BATCH + tid;
+    if (progress < todo_total) {
+      uint32_t id = point_list[range.x + progress];
+      sId[buf][tid] = id;
+      const SplatRecord* r = rec + id;
+      bb_cp_async16(&sA[buf][tid], &r->a);
+      bb_cp_async16(&sB[buf][tid], &r->b);
+      bb_cp_async16(&sC[buf][tid], &r->c);
+    }
+    bb_cp_async_commit();
+  };
+  if (rounds > 0) fetch(0, 0);
+
+  for (int i = 0; i < rounds; i++) {
+    const int buf = i & 1;
+    if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else bb_cp_async_commit();
+    bb_cp_async_wait<1>();
+    __syncthreads();
+    const int nbatch = min(BB_BATCH, (int)todo_total - i * BB_BATCH);
+    const uint32_t base = i * BB_BATCH;
+
+    for (int j = 0; j < nbatch; j++) {
+      const uint32_t e = base + j;
+      const float4 con_o = sA[buf][j];
+      const float4 b = sB[buf][j];
+      float v[10];
+#pragma unroll
+      for (int q = 0; q < 10; q++) v[q] = 0.f;
+      bool any = false;
+      float cg = 0.f, cb = 0.f;   // loaded lazily: only contributing pixels need the colour
+      bool have_c = false;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (e < last[k]) {  // backward.cu:592
+          const float dx = b.x - pxf[k], dy = b.y - pyf[k];
+          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+          if (!(power > 0.0f)) {
+            const float G = exp(power);
+            const float alpha = min(0.99f, con_o.w * G);
+            if (!(alpha < 1.0f / 255.0f)) {
+              any = true;
+              if (!have_c) {
+                const float4 cc = sC[buf][j];
+                cg = cc.x; cb = cc.y;
+                have_c = true;
+              }
+              const float invd = b.z;
+              // c . dL/dC + invd * dL/dD
+              const float cd = b.w * dC0[k] + cg * dC1[k] + cb * dC2[k] + invd * dD[k];
+              const float Tk = T[k];
+              const float weight = alpha * Tk;
+              const float om = 1.0f - alpha;
+              const float inv = __frcp_rn(om);
+              S[k] += weight * cd;
+              const float dL_dalpha = cd * Tk + inv * (S[k] - bgT[k]);
+              T[k] = Tk * om;
+              v[6] += weight * dC0[k];
+              v[7] += weight * dC1[k];
+              v[8] += weight * dC2[k];
+              v[9] += weight * dD[k];
+              const float dL_dG = con_o.w * dL_dalpha;
+              const float gdx = G * dx, gdy = G * dy;
+              const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+              const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+              v[0] += dL_dG * dG_ddelx * ddelx_dx;
+              v[1] += dL_dG * dG_ddely * ddely_dy;
+              v[2] += -0.5f * gdx * dx * dL_dG;
+              v[3] += -0.5f * gdx * dy * dL_dG;
+              v[4] += -0.5f * gdy * dy * dL_dG;
+              v[5] += G * dL_dalpha;
+            }
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+      const float tot = bb_warp_reduce10(v, lane);
+      if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
+    }
+    __syncthreads();
+    // flush the batch: thread t owns splat t
+    if (tid < nbatch) {
+      float a[10];
+      bool nz = false;
+#pragma unroll
+      for (int q = 0; q < 10; q++) {
+        a[q] = sAcc[tid][q];
+        nz |= (a[q] != 0.f);
+        sAcc[tid][q] = 0.f;
+      }
+      if (nz) {
+        float* dst = accum + (size_t)sId[buf][tid] * BB_ACC;
+        bb_red_add_v4(dst, a[0], a[1], a[2], a[3]);
+        bb_red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
+        bb_red_add_v2(dst + 8, a[8], a[9]);
+      }
+    }
+    __syncthreads();
+  }
+  bb_cp_async_wait<0>();
+}
+
+size_t bwd_accum_bytes(size_t P) { return align_up(P * BB_ACC * sizeof(float)); }
+
+int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
+                     const float* dL_dcolor, const float* dL_dinvdepth, float* accum,
+                     cudaStream_t s) {
+  cudaMemsetAsync(accum, 0, (size_t)prm.P * BB_ACC * sizeof(float), s);
+  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
+  blend_bwd_kernel<<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
+                                               im.final_T, im.n_contrib, im.pix_color,
+                                               im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
+                                               prm.ref_bucket_cull_quirk != 0);
+  return check_launch("blend_bwd", prm.debug != 0, s);
+}
+
+}  // namespace dogs

@@ -72,168 +72,6 @@ __device__ __forceinline__ int warp_reduce10_slot(int lane) {
   return 5 * b4 + i1;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
-blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
-                 int H, const float* __restrict__ bg_color, const SplatRecord* __restrict__ rec,
-                 const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-                 const float* __restrict__ pixel_colors, const float* __restrict__ pixel_invdepths,
-                 const float* __restrict__ dL_dpixels, const float* __restrict__ dL_invdepths,
-                 float* __restrict__ accum, bool ref_quirk) {
-  __shared__ float4 sA[2][TILE_PIX];
-  __shared__ float4 sB[2][TILE_PIX];
-  __shared__ float4 sC[2][TILE_PIX];
-  __shared__ uint32_t sId[2][TILE_PIX];
-  __shared__ float sAcc[TILE_PIX][11];
-  __shared__ uint32_t sMax, sMaxRows01;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // warp w covers an 8x4 pixel block so that a splat's footprint hits few warps
-  const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-  const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-  const uint32_t pix_id = W * py + px;
-  const float2 pixf = {(float)px, (float)py};
-  const size_t HW = (size_t)H * W;
-  const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
-
-  uint32_t last_contributor = 0;
-  float T_final = 0.f, dLdC[3] = {0.f, 0.f, 0.f}, dLdD = 0.f, ar[3] = {0.f, 0.f, 0.f}, ard = 0.f;
-  if (inside) {
-    last_contributor = n_contrib[pix_id];
-    T_final = final_Ts[pix_id];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-      dLdC[ch] = dL_dpixels[ch * HW + pix_id];
-      ar[ch] = -pixel_colors[ch * HW + pix_id];
-    }
-    dLdD = dL_invdepths ? dL_invdepths[pix_id] : 0.f;
-    ard = -pixel_invdepths[pix_id];
-  }
-  const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
-  const float bg_dot_dpixel = bg0 * dLdC[0] + bg1 * dLdC[1] + bg2 * dLdC[2];
-  const float ddelx_dx = 0.5 * W;
-  const float ddely_dy = 0.5 * H;
-
-  if (tid == 0) { sMax = 0; sMaxRows01 = 0; }
-#pragma unroll
-  for (int k = 0; k < 11; k++) sAcc[tid][k] = 0.f;
-  __syncthreads();
-  {
-    uint32_t m = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) atomicMax(&sMax, m);
-    // tile-local rows 0-1 (= the first warp of the reference's 16x16 forward block)
-    if (ref_quirk && warp < 2 && lane < 16) atomicMax(&sMaxRows01, last_contributor);
-  }
-  __syncthreads();
-  if (ref_quirk) {
-    // Reference behaviour (see DgrParams::ref_bucket_cull_quirk): buckets of 32 entries whose first
-    // entry is >= max(n_contrib over rows 0-1) contribute nothing.
-    const uint32_t cut = (sMaxRows01 + 31u) & ~31u;
-    last_contributor = min(last_contributor, cut);
-  }
-  const uint32_t todo_total = min(range.y - range.x, ref_quirk ? min(sMax, (sMaxRows01 + 31u) & ~31u) : sMax);  // backward.cu:505-507
-  const int rounds = (todo_total + TILE_PIX - 1) / TILE_PIX;
-  const int my_slot = warp_reduce10_slot(lane);
-
-  auto fetch = [&](int round, int buf) {
-    uint32_t progress = round * TILE_PIX + tid;
-    if (progress < todo_total) {
-      uint32_t id = point_list[range.x + progress];
-      sId[buf][tid] = id;
-      const SplatRecord* r = rec + id;
-      cp_async16(&sA[buf][tid], &r->a);
-      cp_async16(&sB[buf][tid], &r->b);
-      cp_async16(&sC[buf][tid], &r->c);
-    }
-    cp_async_commit();
-  };
-  if (rounds > 0) fetch(0, 0);
-
-  float T = 1.0f;
-  for (int i = 0; i < rounds; i++) {
-    const int buf = i & 1;
-    if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const int nbatch = min(TILE_PIX, (int)todo_total - i * TILE_PIX);
-    const uint32_t base = i * TILE_PIX;
-
-    for (int j = 0; j < nbatch; j++) {
-      float v[10];
-#pragma unroll
-      for (int k = 0; k < 10; k++) v[k] = 0.f;
-      bool contrib = false;
-      if (base + j < last_contributor) {  // backward.cu:592
-        const float4 con_o = sA[buf][j];
-        const float4 b = sB[buf][j];
-        const float2 d = {b.x - pixf.x, b.y - pixf.y};
-        const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-        if (!(power > 0.0f)) {
-          const float G = exp(power);
-          const float alpha = min(0.99f, con_o.w * G);
-          if (!(alpha < 1.0f / 255.0f)) {
-            contrib = true;
-            const float4 cc = sC[buf][j];
-            const float c[3] = {b.w, cc.x, cc.y};
-            const float invd = b.z;
-            const float weight = alpha * T;
-            float dL_dalpha = 0.0f;
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-              ar[ch] += weight * c[ch];
-              v[6 + ch] = weight * dLdC[ch];
-              dL_dalpha += ((c[ch] * T) - (1.0f / (1.0f - alpha)) * (-ar[ch])) * dLdC[ch];
-            }
-            ard += weight * invd;
-            v[9] = weight * dLdD;
-            dL_dalpha += ((invd * T) - (1.0f / (1.0f - alpha)) * (-ard)) * dLdD;
-            dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
-            T *= (1.0f - alpha);
-            const float dL_dG = con_o.w * dL_dalpha;
-            const float gdx = G * d.x;
-            const float gdy = G * d.y;
-            const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-            const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-            v[0] = dL_dG * dG_ddelx * ddelx_dx;
-            v[1] = dL_dG * dG_ddely * ddely_dy;
-            v[2] = -0.5f * gdx * d.x * dL_dG;
-            v[3] = -0.5f * gdx * d.y * dL_dG;
-            v[4] = -0.5f * gdy * d.y * dL_dG;
-            v[5] = G * dL_dalpha;
-          }
-        }
-      }
-      if (!__any_sync(0xffffffffu, contrib)) continue;
-      const float tot = warp_reduce10(v, lane);
-      if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
-    }
-    __syncthreads();
-    // flush the batch: thread t owns splat t
-    if (tid < nbatch) {
-      float a[10];
-      bool any = false;
-#pragma unroll
-      for (int k = 0; k < 10; k++) {
-        a[k] = sAcc[tid][k];
-        any |= (a[k] != 0.f);
-        sAcc[tid][k] = 0.f;
-      }
-      if (any) {
-        float* dst = accum + (size_t)sId[buf][tid] * ACC_STRIDE;
-        red_add_v4(dst, a[0], a[1], a[2], a[3]);
-        red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
-        red_add_v2(dst + 8, a[8], a[9]);
-      }
-    }
-    // the barrier at the top of the next round (after its fetch) orders sAcc / sId reuse
-    __syncthreads();
-  }
-  cp_async_wait<0>();
-}
-
 // ---- backward.cu:23-144 ---------------------------------------------------------------
 // sh_row: this Gaussian's staged SH "rest" row (3*M floats in shared memory); it is overwritten
 // with dL_dsh so the CTA can store the whole slice with coalesced 16-byte writes.
@@ -573,19 +411,6 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   }
 }
 
-size_t bwd_accum_bytes(size_t P) { return align_up(P * ACC_STRIDE * sizeof(float)); }
-
-int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
-                     const float* dL_dcolor, const float* dL_dinvdepth, float* accum,
-                     cudaStream_t s) {
-  cudaMemsetAsync(accum, 0, (size_t)prm.P * ACC_STRIDE * sizeof(float), s);
-  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
-  blend_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
-                                             im.final_T, im.n_contrib, im.pix_color,
-                                             im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
-                                             prm.ref_bucket_cull_quirk != 0);
-  return check_launch("blend_bwd", prm.debug != 0, s);
-}
 
 int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const float* dc,
                           const float* sh, const float* opacities, const float* scales,
