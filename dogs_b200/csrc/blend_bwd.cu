@@ -9,10 +9,11 @@
 // Work layout (second version; ncu of the first version — one pixel per thread — showed the
 // kernel issue-bound with ~45 % of its instructions in the cross-lane reduction of the 10
 // gradient terms, profiles/r1_full_v1_kernels.md):
-//   * one CTA of 64 threads per 16x16 tile; each thread owns a 2x2 pixel quad, a warp a 16x8
-//     half tile.  The four pixels of a thread share the record loads and are summed in
-//     registers before anything crosses lanes, so the reduction runs once per (half tile, splat)
-//     instead of once per (32 pixels, splat);
+//   * one CTA of 64 threads per 16x16 tile; a warp owns an 8x16 half tile, each thread 4 pixels
+//     (one in each 8x4 block of the half tile).  The four pixels of a thread share the record
+//     loads and are summed in registers before anything crosses lanes, so the reduction runs once
+//     per (half tile, splat) instead of once per (32 pixels, splat), while the heavy gradient
+//     math still runs per compact 8x4 block and is skipped for blocks the splat does not reach;
 //   * the colour/depth prefix of the reference (ar[3], ard) is carried as ONE scalar
 //     S = sum_c ar_c * dL/dC_c + ard * dL/dD, which removes 3/4 of the per-pair state updates:
 //       dL/dalpha = T * (c . dL/dC + invd * dL/dD) + S / (1 - alpha)  - T_final * bg.dL/dC / (1 - alpha);
@@ -92,21 +93,23 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ uint32_t sMax, sMaxRows01;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // thread -> 2x2 quad: warp w covers tile rows 8w..8w+7, lane (lx, ly) = (lane & 7, lane >> 3)
-  const uint32_t qx = blockIdx.x * TILE_X + 2 * (lane & 7);
-  const uint32_t qy = blockIdx.y * TILE_Y + 8 * warp + 2 * (lane >> 3);
+  // warp w covers tile columns 8w..8w+7 (8 wide, 16 tall); pixel k of lane (lx, ly) = (lane & 7, lane >> 3)
+  // is (8w + lx, 4k + ly): the 32 pixels that a warp treats together in step k form a compact 8x4
+  // block, so a splat that misses the block costs the warp nothing but the test.
+  const uint32_t qx = blockIdx.x * TILE_X + 8 * warp + (lane & 7);
+  const uint32_t qy = blockIdx.y * TILE_Y + (lane >> 3);
   const size_t HW = (size_t)H * W;
   const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
   const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
   const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
-  // per-pixel state (k = 2*dy + dx)
+  // per-pixel state (k = 8x4 block index, top to bottom)
   uint32_t last[4];
   float T[4], S[4], dC0[4], dC1[4], dC2[4], dD[4], bgT[4], pxf[4], pyf[4];
   uint32_t lmax = 0, lmax01 = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const uint32_t px = qx + (k & 1), py = qy + (k >> 1);
+    const uint32_t px = qx, py = qy + 4 * k;
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     pxf[k] = (float)px;
     pyf[k] = (float)py;
@@ -126,7 +129,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
     lmax = max(lmax, last[k]);
     // rows 0-1 of the tile = the first warp of the reference's 16x16 forward block
-    if (warp == 0 && (lane >> 3) == 0) lmax01 = max(lmax01, last[k]);
+    if (k == 0 && (lane >> 3) < 2) lmax01 = max(lmax01, last[k]);
   }
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
@@ -183,56 +186,54 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const uint32_t e = base + j;
       const float4 con_o = sA[buf][j];
       const float4 b = sB[buf][j];
+      // Test the four pixels branch-free (independent chains => ILP); the alpha/T thresholds are the
+      // forward's own expressions, so the contribution decisions are identical to the forward pass.
+      float dx[4], dy[4], G[4], al[4];
+      bool c[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        dx[k] = b.x - pxf[k];
+        dy[k] = b.y - pyf[k];
+        const float power = -0.5f * (con_o.x * dx[k] * dx[k] + con_o.z * dy[k] * dy[k]) - con_o.y * dx[k] * dy[k];
+        G[k] = exp(power);
+        al[k] = min(0.99f, con_o.w * G[k]);
+        c[k] = (e < last[k]) && !(power > 0.0f) && !(al[k] < 1.0f / 255.0f);   // backward.cu:592-600
+      }
+      if (!__any_sync(0xffffffffu, c[0] | c[1] | c[2] | c[3])) continue;
+      const float4 cc = sC[buf][j];
+      const float invd = b.z;
       float v[10];
 #pragma unroll
       for (int q = 0; q < 10; q++) v[q] = 0.f;
-      bool any = false;
-      float cg = 0.f, cb = 0.f;   // loaded lazily: only contributing pixels need the colour
-      bool have_c = false;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        if (e < last[k]) {  // backward.cu:592
-          const float dx = b.x - pxf[k], dy = b.y - pyf[k];
-          const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
-          if (!(power > 0.0f)) {
-            const float G = exp(power);
-            const float alpha = min(0.99f, con_o.w * G);
-            if (!(alpha < 1.0f / 255.0f)) {
-              any = true;
-              if (!have_c) {
-                const float4 cc = sC[buf][j];
-                cg = cc.x; cb = cc.y;
-                have_c = true;
-              }
-              const float invd = b.z;
-              // c . dL/dC + invd * dL/dD
-              const float cd = b.w * dC0[k] + cg * dC1[k] + cb * dC2[k] + invd * dD[k];
-              const float Tk = T[k];
-              const float weight = alpha * Tk;
-              const float om = 1.0f - alpha;
-              const float inv = __frcp_rn(om);
-              S[k] += weight * cd;
-              const float dL_dalpha = cd * Tk + inv * (S[k] - bgT[k]);
-              T[k] = Tk * om;
-              v[6] += weight * dC0[k];
-              v[7] += weight * dC1[k];
-              v[8] += weight * dC2[k];
-              v[9] += weight * dD[k];
-              const float dL_dG = con_o.w * dL_dalpha;
-              const float gdx = G * dx, gdy = G * dy;
-              const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-              const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-              v[0] += dL_dG * dG_ddelx * ddelx_dx;
-              v[1] += dL_dG * dG_ddely * ddely_dy;
-              v[2] += -0.5f * gdx * dx * dL_dG;
-              v[3] += -0.5f * gdx * dy * dL_dG;
-              v[4] += -0.5f * gdy * dy * dL_dG;
-              v[5] += G * dL_dalpha;
-            }
-          }
-        }
+        if (!__any_sync(0xffffffffu, c[k])) continue;       // warp-uniform: this 8x4 block is not reached
+        const float alpha = c[k] ? al[k] : 0.f;              // masked lanes: weight 0, T and S unchanged
+        const float Gk = c[k] ? G[k] : 0.f;                  // (exp(power) may be inf where power > 0)
+        // c . dL/dC + invd * dL/dD
+        const float cd = b.w * dC0[k] + cc.x * dC1[k] + cc.y * dC2[k] + invd * dD[k];
+        const float Tk = T[k];
+        const float weight = alpha * Tk;
+        const float om = 1.0f - alpha;
+        const float inv = __frcp_rn(om);
+        S[k] += weight * cd;
+        const float dL_dalpha = c[k] ? (cd * Tk + inv * (S[k] - bgT[k])) : 0.f;
+        T[k] = Tk * om;
+        v[6] += weight * dC0[k];
+        v[7] += weight * dC1[k];
+        v[8] += weight * dC2[k];
+        v[9] += weight * dD[k];
+        const float dL_dG = con_o.w * dL_dalpha;
+        const float gdx = Gk * dx[k], gdy = Gk * dy[k];
+        const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+        const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+        v[0] += dL_dG * dG_ddelx * ddelx_dx;
+        v[1] += dL_dG * dG_ddely * ddely_dy;
+        v[2] += -0.5f * gdx * dx[k] * dL_dG;
+        v[3] += -0.5f * gdx * dy[k] * dL_dG;
+        v[4] += -0.5f * gdy * dy[k] * dL_dG;
+        v[5] += Gk * dL_dalpha;
       }
-      if (!__any_sync(0xffffffffu, any)) continue;
       const float tot = bb_warp_reduce10(v, lane);
       if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
     }
