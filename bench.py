@@ -242,13 +242,18 @@ def main():
     with ClockSampler(local_rank) as clk:
         barrier()
         ev0.record()
+        marks = [ev0]
         for _ in range(K):
             step(sc, target)
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
         if admm is not None:
             admm.consensus()
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
     launches = (lib.dogs_launch_count() - n0) if lib else 0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if distributed:
@@ -305,6 +310,7 @@ def main():
                        "l2_policy": "inputs (708 MB of Gaussian parameters + 10 M instance lists) exceed the 126 MB L2",
                        "blocks": world if args.impl == "ours" else 1},
             "gpu_launches": int(launches), "clocks": clk.summary(),
+            "step_ms": {"min": per_step[0], "median": per_step[K // 2], "max": per_step[-1]},
         }
         if args.impl == "reference":
             out["impl"] = "reference"

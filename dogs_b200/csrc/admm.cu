@@ -3,109 +3,158 @@
 //   slave_gaussian_trainer.py:99-121 (dual update) and :161-202 (penalty terms)
 // for one scene block per GPU.  Only Gaussians owned by more than one block travel: they are
 // packed into a dense [S_total, 59] buffer, summed across ranks with ONE NCCL all-reduce, and
-// unpacked by a kernel that also applies the dual update and accumulates the residual sums, so
-// the 59 floats of a Gaussian are read and written once per consensus round.
+// unpacked by kernels that also apply the dual update and accumulate the residual sums, so the
+// 59 floats of a Gaussian are read and written once per consensus round.
 //
 // A Gaussian = 59 floats in 6 tensors: xyz 3, f_dc 3, f_rest 45, scaling 3, quaternion 4, opacity 1
 // (raw, pre-activation values are the consensus variables).
+//
+// All kernels are HBM-bound element-wise passes: every tensor is walked as a flat array with
+// consecutive threads on consecutive elements (16-byte accesses in the per-iteration penalty
+// kernel); per-group sums are kept in FP64.
 #include "common.cuh"
 
 namespace dogs {
 
 constexpr int ADMM_ROW = 59;
-__device__ __forceinline__ int admm_group_of(int e) {
-  return e < 3 ? 0 : e < 6 ? 1 : e < 51 ? 2 : e < 54 ? 3 : e < 58 ? 4 : e < 59 ? 5 : -1;
-}
-__constant__ int ADMM_START[6] = {0, 3, 6, 51, 54, 58};
-__constant__ int ADMM_SIZE[6] = {3, 3, 45, 3, 4, 1};
+constexpr int ADMM_THREADS = 256;
 
-struct Ptrs6 { float* g[6]; };
-struct CPtrs6 { const float* g[6]; };
+struct PenaltyArgs {
+  const float* x[6];
+  const float* u[6];
+  const float* z[6];
+  float* grad[6];
+  unsigned long long chunk_end[6];   // exclusive prefix ends, in float4 chunks
+  unsigned long long len[6];         // elements per tensor
+  float coef[6];
+};
 
-// blockDim = (64, 4): x = element of the 59-float row, y = Gaussian within the CTA.
-__global__ void __launch_bounds__(256)
-admm_pack_kernel(CPtrs6 x, const int64_t* __restrict__ local_idx, const int64_t* __restrict__ slot,
-                 int64_t S, float* __restrict__ sendbuf) {
-  const int e = threadIdx.x;
-  const int g = admm_group_of(e);
-  if (g < 0) return;
-  const int off = e - ADMM_START[g], sz = ADMM_SIZE[g];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < S; i += (int64_t)gridDim.x * blockDim.y)
-    sendbuf[slot[i] * ADMM_ROW + e] = x.g[g][local_idx[i] * sz + off];
+__device__ __forceinline__ double block_sum_to(double v, double* smem_slot) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(smem_slot, v);
+  return v;
 }
 
-__global__ void __launch_bounds__(256)
-admm_unpack_update_kernel(CPtrs6 x, Ptrs6 u, Ptrs6 z, const int64_t* __restrict__ slot_of_local,
-                          const float* __restrict__ inv_count, int64_t n,
-                          const float* __restrict__ recvbuf, float relax, double* __restrict__ residuals) {
-  __shared__ double acc[12];
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid < 12) acc[tid] = 0.0;
-  __syncthreads();
-  const int e = threadIdx.x;
-  const int g = admm_group_of(e);
-  double primal = 0.0, dual = 0.0;
-  if (g >= 0) {
-    const int off = e - ADMM_START[g], sz = ADMM_SIZE[g];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < n; i += (int64_t)gridDim.x * blockDim.y) {
-      const int64_t k = i * sz + off;
-      const int64_t sl = slot_of_local[i];
-      const float xv = x.g[g][k];
-      const float z_old = z.g[g][k];
-      float z_new;
-      if (sl >= 0) {
-        const float w = inv_count[i];
-        z_new = recvbuf[sl * ADMM_ROW + e] * w;            // master:551-555 average_gaussians
-        u.g[g][k] += relax * (xv - z_new);                 // slave:99-121
-        const float dp = z_new - xv;
-        primal += (double)dp * dp;                         // master:396-432
-        const float dd = z_old - z_new;
-        dual += (double)w * ((double)dd * dd);             // master:435-456 (each global Gaussian once)
-      } else {
-        z_new = xv;                                        // count == 1: z == x, u unchanged
-        const float dd = z_old - z_new;
-        dual += (double)dd * dd;
-      }
-      z.g[g][k] = z_new;
-    }
-  }
-  if (g >= 0) {
-    atomicAdd(&acc[g], primal);
-    atomicAdd(&acc[6 + g], dual);
-  }
-  __syncthreads();
-  if (tid < 12 && acc[tid] != 0.0) atomicAdd(&residuals[tid], acc[tid]);
-}
-
-__global__ void __launch_bounds__(256)
-admm_penalty_kernel(CPtrs6 x, CPtrs6 u, CPtrs6 z, Ptrs6 grad, int64_t n, float c0, float c1, float c2,
-                    float c3, float c4, float c5, double* __restrict__ sums) {
+// One launch for all six tensors: r = x + u - z;  sums[g] += sum r^2;  grad += coef[g] * r.
+__global__ void __launch_bounds__(ADMM_THREADS)
+admm_penalty_kernel(const __grid_constant__ PenaltyArgs a, double* __restrict__ sums) {
   __shared__ double acc[6];
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid < 6) acc[tid] = 0.0;
+  if (threadIdx.x < 6) acc[threadIdx.x] = 0.0;
   __syncthreads();
-  const int e = threadIdx.x;
-  const int g = admm_group_of(e);
-  double s = 0.0;
-  if (g >= 0) {
-    const float coef = g == 0 ? c0 : g == 1 ? c1 : g == 2 ? c2 : g == 3 ? c3 : g == 4 ? c4 : c5;
-    const int off = e - ADMM_START[g], sz = ADMM_SIZE[g];
-    float* gr = grad.g[g];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < n; i += (int64_t)gridDim.x * blockDim.y) {
-      const int64_t k = i * sz + off;
-      const float r = (x.g[g][k] + u.g[g][k]) - z.g[g][k];   // mse_loss(x + u, z), slave:169-187
-      s += (double)r * r;
-      if (gr) gr[k] += coef * r;                              // d/dx 0.5*rho*mean(r^2) = rho/numel * r
+  const unsigned long long total = a.chunk_end[5];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  double part = 0.0;      // running sum of the group this thread is currently in
+  int part_g = 0;
+  for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+    int g = 0;
+#pragma unroll
+    for (int q = 0; q < 5; q++) g += (c >= a.chunk_end[q]) ? 1 : 0;
+    const unsigned long long lc = c - (g ? a.chunk_end[g - 1] : 0ull);
+    const unsigned long long e0 = lc * 4;
+    const float coef = a.coef[g];
+    const float* __restrict__ xp = a.x[g];
+    const float* __restrict__ up = a.u[g];
+    const float* __restrict__ zp = a.z[g];
+    float* __restrict__ gp = a.grad[g];
+    float s = 0.f;
+    if (e0 + 4 <= a.len[g]) {
+      const float4 xv = *reinterpret_cast<const float4*>(xp + e0);
+      const float4 uv = *reinterpret_cast<const float4*>(up + e0);
+      const float4 zv = *reinterpret_cast<const float4*>(zp + e0);
+      const float r0 = (xv.x + uv.x) - zv.x, r1 = (xv.y + uv.y) - zv.y;   // mse_loss(x + u, z), slave:169-187
+      const float r2 = (xv.z + uv.z) - zv.z, r3 = (xv.w + uv.w) - zv.w;
+      s = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+      if (gp) {
+        float4 gv = *reinterpret_cast<float4*>(gp + e0);
+        gv.x += coef * r0; gv.y += coef * r1; gv.z += coef * r2; gv.w += coef * r3;   // rho/numel * r
+        *reinterpret_cast<float4*>(gp + e0) = gv;
+      }
+    } else {
+      for (unsigned long long e = e0; e < a.len[g]; e++) {
+        const float r = (xp[e] + up[e]) - zp[e];
+        s += r * r;
+        if (gp) gp[e] += coef * r;
+      }
     }
-    atomicAdd(&acc[g], s);
+    if (g != part_g) {      // rare: the grid-stride walk crossed into the next tensor
+      if (part != 0.0) atomicAdd(&acc[part_g], part);
+      part = 0.0;
+      part_g = g;
+    }
+    part += (double)s;
   }
+  if (part != 0.0) atomicAdd(&acc[part_g], part);
   __syncthreads();
-  if (tid < 6 && acc[tid] != 0.0) atomicAdd(&sums[tid], acc[tid]);
+  if (threadIdx.x < 6 && acc[threadIdx.x] != 0.0) atomicAdd(&sums[threadIdx.x], acc[threadIdx.x]);
 }
 
-static int grid_for(int64_t rows) {
-  int64_t g = (rows + 3) / 4;
-  const int64_t cap = 148 * 8;
+// sendbuf[slot[i]*59 + START + off] = x[local_idx[i]*SZ + off], flat over the S*SZ elements of one group
+template <int SZ>
+__global__ void __launch_bounds__(ADMM_THREADS)
+admm_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ local_idx,
+                 const int64_t* __restrict__ slot, unsigned long long total, int start,
+                 float* __restrict__ sendbuf) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const unsigned long long i = e / SZ;
+    const int off = (int)(e - i * SZ);
+    sendbuf[slot[i] * ADMM_ROW + start + off] = x[local_idx[i] * SZ + off];
+  }
+}
+
+// Over ALL n Gaussians of the block (flat over n*SZ elements of one group):
+//   shared (slot >= 0): z = recv * inv_count (master:551-555); u += relax*(x - z) (slave:99-121)
+//   single-owner      : z = x, u untouched
+//   residuals[g] += sum (z - x)^2 (primal, master:396-432); residuals[6+g] += sum inv_count*(z_prev - z)^2 (dual, :435-456)
+template <int SZ>
+__global__ void __launch_bounds__(ADMM_THREADS)
+admm_unpack_kernel(const float* __restrict__ x, float* __restrict__ u, float* __restrict__ z,
+                   const int64_t* __restrict__ slot_of_local, const float* __restrict__ inv_count,
+                   unsigned long long total, int start, const float* __restrict__ recvbuf, float relax,
+                   double* __restrict__ residuals, int g) {
+  __shared__ double acc[2];
+  if (threadIdx.x < 2) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  double primal = 0.0, dual = 0.0;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const unsigned long long i = e / SZ;
+    const int off = (int)(e - i * SZ);
+    const int64_t sl = slot_of_local[i];
+    const float xv = x[e];
+    const float z_old = z[e];
+    float z_new;
+    if (sl >= 0) {
+      const float w = inv_count[i];
+      z_new = recvbuf[sl * ADMM_ROW + start + off] * w;
+      u[e] += relax * (xv - z_new);
+      const float dp = z_new - xv;
+      primal += (double)dp * dp;
+      const float dd = z_old - z_new;
+      dual += (double)w * ((double)dd * dd);
+    } else {
+      z_new = xv;
+      const float dd = z_old - z_new;
+      dual += (double)dd * dd;
+    }
+    z[e] = z_new;
+  }
+  block_sum_to(primal, &acc[0]);
+  block_sum_to(dual, &acc[1]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (acc[0] != 0.0) atomicAdd(&residuals[g], acc[0]);
+    if (acc[1] != 0.0) atomicAdd(&residuals[6 + g], acc[1]);
+  }
+}
+
+static const int kSize[6] = {3, 3, 45, 3, 4, 1};
+static const int kStart[6] = {0, 3, 6, 51, 54, 58};
+
+static int grid_for(unsigned long long work_items) {
+  unsigned long long g = (work_items + ADMM_THREADS - 1) / ADMM_THREADS;
+  const unsigned long long cap = 148ull * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -118,12 +167,14 @@ extern "C" int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, co
   cudaStream_t s = (cudaStream_t)stream;
   if (!sendbuf && S_total > 0) { set_error("admm_pack: null send buffer"); return 1; }
   if (zero_fill && S_total > 0) cudaMemsetAsync(sendbuf, 0, (size_t)S_total * ADMM_ROW * sizeof(float), s);
-  if (S <= 0) return check_launch("admm_pack", false, s);
+  if (S <= 0) return check_launch("admm_pack", false, s, 0);
   if (!x || !local_idx || !slot) { set_error("admm_pack: null pointer"); return 1; }
-  CPtrs6 xp;
-  for (int g = 0; g < 6; g++) xp.g[g] = x->g[g];
-  admm_pack_kernel<<<grid_for(S), dim3(64, 4), 0, s>>>(xp, local_idx, slot, S, sendbuf);
-  return check_launch("admm_pack", false, s);
+#define PACK(G, SZ)                                                                                   \
+  admm_pack_kernel<SZ><<<grid_for((unsigned long long)S * SZ), ADMM_THREADS, 0, s>>>(                 \
+      x->g[G], local_idx, slot, (unsigned long long)S * SZ, kStart[G], sendbuf)
+  PACK(0, 3); PACK(1, 3); PACK(2, 45); PACK(3, 3); PACK(4, 4); PACK(5, 1);
+#undef PACK
+  return check_launch("admm_pack", false, s, 6);
 }
 
 extern "C" int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
@@ -132,11 +183,13 @@ extern "C" int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* 
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
   if (!x || !u || !z || !slot_of_local || !inv_count || !residuals) { set_error("admm_unpack_update: null pointer"); return 1; }
-  CPtrs6 xp; Ptrs6 up, zp;
-  for (int g = 0; g < 6; g++) { xp.g[g] = x->g[g]; up.g[g] = u->g[g]; zp.g[g] = z->g[g]; }
-  admm_unpack_update_kernel<<<grid_for(n), dim3(64, 4), 0, s>>>(xp, up, zp, slot_of_local, inv_count, n,
-                                                                recvbuf, relax, residuals);
-  return check_launch("admm_unpack_update", false, s);
+#define UNPACK(G, SZ)                                                                                 \
+  admm_unpack_kernel<SZ><<<grid_for((unsigned long long)n * SZ), ADMM_THREADS, 0, s>>>(               \
+      x->g[G], u->g[G], z->g[G], slot_of_local, inv_count, (unsigned long long)n * SZ, kStart[G], recvbuf, \
+      relax, residuals, G)
+  UNPACK(0, 3); UNPACK(1, 3); UNPACK(2, 45); UNPACK(3, 3); UNPACK(4, 4); UNPACK(5, 1);
+#undef UNPACK
+  return check_launch("admm_unpack_update", false, s, 6);
 }
 
 extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u, const AdmmConstTensors* z,
@@ -145,12 +198,18 @@ extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
   if (!x || !u || !z || !coef || !sums) { set_error("admm_penalty: null pointer"); return 1; }
-  CPtrs6 xp, up, zp; Ptrs6 gp;
+  PenaltyArgs a;
+  unsigned long long end = 0;
   for (int g = 0; g < 6; g++) {
-    xp.g[g] = x->g[g]; up.g[g] = u->g[g]; zp.g[g] = z->g[g];
-    gp.g[g] = grad ? grad->g[g] : nullptr;
+    a.x[g] = x->g[g]; a.u[g] = u->g[g]; a.z[g] = z->g[g];
+    a.grad[g] = grad ? grad->g[g] : nullptr;
+    a.len[g] = (unsigned long long)n * kSize[g];
+    end += (a.len[g] + 3) / 4;
+    a.chunk_end[g] = end;
+    a.coef[g] = coef[g];
+    const uintptr_t al = (uintptr_t)a.x[g] | (uintptr_t)a.u[g] | (uintptr_t)a.z[g] | (uintptr_t)a.grad[g];
+    if (al & 15) { set_error("admm_penalty: tensors must be 16-byte aligned"); return 1; }
   }
-  admm_penalty_kernel<<<grid_for(n), dim3(64, 4), 0, s>>>(xp, up, zp, gp, n, coef[0], coef[1], coef[2],
-                                                          coef[3], coef[4], coef[5], sums);
+  admm_penalty_kernel<<<grid_for(end), ADMM_THREADS, 0, s>>>(a, sums);
   return check_launch("admm_penalty", false, s);
 }

@@ -33,7 +33,7 @@ int check_launch(const char* what, bool debug, cudaStream_t s, int kernels) {
 size_t GeomState::bytes(size_t P) {
   Carver c(nullptr);
   c.take<SplatRecord>(P); c.take<uint8_t>(P); c.take<uint32_t>(P); c.take<uint32_t>(P);
-  c.take<uint32_t>(P); c.take<uint32_t>(P);
+  c.take<uint32_t>(P); c.take<uint32_t>(P); c.take<unsigned long long>(P);
   return c.off;
 }
 GeomState GeomState::carve(char* p, size_t P) {
@@ -45,6 +45,7 @@ GeomState GeomState::carve(char* p, size_t P) {
   g.depth_key = c.take<uint32_t>(P);
   g.sorted_idx = c.take<uint32_t>(P);
   g.offsets = c.take<uint32_t>(P);
+  g.tile_mask = c.take<unsigned long long>(P);
   return g;
 }
 size_t BinState::bytes(size_t R) {

@@ -152,6 +152,7 @@ struct GeomState {
   SplatRecord* rec; uint8_t* clamped; uint32_t* tiles; uint32_t* depth_key;
   uint32_t* sorted_idx;    // Gaussian ids in depth order
   uint32_t* offsets;       // exclusive scan of tiles in depth order
+  unsigned long long* tile_mask;  // reachable tiles of the rect (bit = row-major index), rect area <= 64
   static size_t bytes(size_t P);
   static GeomState carve(char* p, size_t P);
 };

@@ -102,8 +102,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
                       int* __restrict__ radii, SplatRecord* __restrict__ rec,
                       uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
-                      uint32_t* __restrict__ depth_key, uint32_t gx, uint32_t gy, bool prefiltered,
-                      bool antialiasing) {
+                      uint32_t* __restrict__ depth_key, unsigned long long* __restrict__ tile_mask,
+                      uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing) {
   extern __shared__ float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
   const int first = blockIdx.x * PRE_THREADS;
@@ -127,6 +127,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
   int radius_out = 0;
   uint32_t ntiles = 0, dkey = 0xffffffffu;
+  unsigned long long mask = 0ull;
   do {
     float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
     // auxiliary.h:150-175 in_frustum
@@ -198,13 +199,19 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
     // rasterizer_impl.cu:151-177: count the tiles of the rect the Gaussian can actually reach.
     const float thr = logf(co.w / (1.0f / 255.0f));
+    const int rw = rect_max.x - rect_min.x;
+    const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64;   // mask of reachable tiles fits 64 bits
     for (int y = rect_min.y; y < (int)rect_max.y; y++)
       for (int x = rect_min.x; x < (int)rect_max.x; x++)
-        ntiles += tile_reachable(co, point_image, x, y, thr) ? 1u : 0u;
+        if (tile_reachable(co, point_image, x, y, thr)) {
+          ntiles++;
+          if (small) mask |= 1ull << ((y - (int)rect_min.y) * rw + (x - (int)rect_min.x));
+        }
     dkey = __float_as_uint(depth);
   } while (0);
   radii[idx] = radius_out;
   tiles[idx] = ntiles;
+  tile_mask[idx] = mask;
   depth_key[idx] = ntiles ? dkey : 0xffffffffu;
 }
 
@@ -215,6 +222,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t* __restrict__ sorted_idx,
                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ tiles,
+                      const unsigned long long* __restrict__ tile_mask,
                       const SplatRecord* __restrict__ rec, const int* __restrict__ radii,
                       uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, uint32_t gx,
                       uint32_t gy) {
@@ -223,11 +231,25 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ sorted_idx,
   const uint32_t idx = sorted_idx[i];
   if (tiles[idx] == 0) return;
   uint32_t off = offsets[i];
-  const float4 co = rec[idx].a;
   const float4 b = rec[idx].b;
   const float2 xy = {b.x, b.y};
   uint2 rect_min, rect_max;
   get_rect(xy, radii[idx], rect_min, rect_max, gx, gy);
+  const int rw = rect_max.x - rect_min.x;
+  if (rw * (int)(rect_max.y - rect_min.y) <= 64) {
+    // common case: preprocess already recorded which tiles of the rect are reachable
+    unsigned long long m = tile_mask[idx];
+    while (m) {
+      const int bit = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const int ty = bit / rw, tx = bit - ty * rw;
+      tile_keys[off] = (rect_min.y + ty) * gx + rect_min.x + tx;
+      vals[off] = idx;
+      off++;
+    }
+    return;
+  }
+  const float4 co = rec[idx].a;
   const float thr = logf(co.w / (1.0f / 255.0f));
   for (int y = rect_min.y; y < (int)rect_max.y; y++)
     for (int x = rect_min.x; x < (int)rect_max.x; x++)
@@ -442,7 +464,7 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
       prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
       cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
       prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
-      gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
+      g.tile_mask, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
   return check_launch("preprocess_fwd", prm.debug != 0, s);
 }
 
@@ -450,7 +472,8 @@ int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, 
                 uint32_t* vals, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   emit_instances_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_idx, g.offsets, g.tiles,
-                                                            g.rec, radii, tile_keys, vals, gx, gy);
+                                                            g.tile_mask, g.rec, radii, tile_keys, vals,
+                                                            gx, gy);
   return check_launch("emit_instances", prm.debug != 0, s);
 }
 
