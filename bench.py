@@ -49,46 +49,70 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML in-process
+    (nvidia_ml_py).  Spawning `nvidia-smi` from the benchmark process stalls kernel launches for tens of
+    milliseconds (fork of a CUDA process + driver locks), so it is only the fallback, used once
+    before the region starts."""
 
-    def __init__(self, index):
-        self.index = index
-        self.samples = []
-        self.reasons = set()
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, index, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
         self._stop = threading.Event()
-        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # pylint: disable=W0703
+            self._smi_once()
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append((float(f[0]), float(f[1])))
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
-            except Exception:  # pylint: disable=W0703
-                pass
-            self._stop.wait(0.2)
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+            f = [float(x) for x in out.strip().split(",")]
+            self.samples.append(f[0])
+            self.sm_max = f[1]
+        except Exception:  # pylint: disable=W0703
+            pass
+
+    def sample(self):
+        """One NVML read (a few hundred microseconds of host time).  Called from the benchmark loop
+        itself between steps, while the GPU still has queued work: a sampling thread or a background
+        `nvidia-smi -lms` was measured to stall kernel launches for 20-140 ms per query."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:  # pylint: disable=W0703
+            pass
 
     def __enter__(self):
-        self.thread.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self.thread.join(timeout=6)
+        return False
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
-                "reasons": sorted(self.reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi (before the region)"}
 
 
 def load_modules(impl):
@@ -154,6 +178,7 @@ def main():
     ap.add_argument("--cfg", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not query NVML inside the timed region")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3)
 
@@ -243,8 +268,10 @@ def main():
         barrier()
         ev0.record()
         marks = [ev0]
-        for _ in range(K):
+        for it in range(K):
             step(sc, target)
+            if not args.no_clocks and it in (K // 3, (2 * K) // 3):
+                clk.sample()                          # clocks / throttle reasons under load
             m = torch.cuda.Event(enable_timing=True)
             m.record()
             marks.append(m)

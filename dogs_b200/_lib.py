@@ -110,17 +110,24 @@ def stream_ptr(device=None):
 
 class Allocator:
     """Allocation callback backed by torch's caching allocator (mirrors resizeFunctional,
-    rasterize_points.cu:30-36).  Keeps every buffer it hands out alive in `self.buffers`."""
+    rasterize_points.cu:30-36).  Keeps every buffer it hands out alive in `self.buffers`.
+
+    The ctypes callback closes over the buffer list only — not over `self` — so there is no reference
+    cycle: when the Allocator goes out of scope its buffers return to the caching allocator at once
+    (a cycle would keep hundreds of MB per step alive until Python's cyclic GC runs, forcing fresh
+    cudaMallocs and multi-millisecond stalls)."""
 
     def __init__(self, device):
+        buffers = []
         self.device = device
-        self.buffers = []
-        self.cb = ALLOC_FN(self._alloc)
+        self.buffers = buffers
 
-    def _alloc(self, _user, nbytes):
-        t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
-        self.buffers.append(t)
-        return t.data_ptr()
+        def _alloc(_user, nbytes, _buffers=buffers, _device=device):
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_device)
+            _buffers.append(t)
+            return t.data_ptr()
+
+        self.cb = ALLOC_FN(_alloc)
 
     @property
     def last(self):

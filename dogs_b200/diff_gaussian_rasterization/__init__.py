@@ -107,6 +107,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 else:
                     L.check(L.lib().dgr_forward(*args))
             num_rendered = info.num_rendered
+            scratch.buffers.clear()      # stream-ordered: safe to hand back to the caching allocator now
             del keep
         else:
             color.zero_(); invdepth.zero_()
