@@ -19,7 +19,7 @@
 //       dL/dalpha = T * (c . dL/dC + invd * dL/dD) + S / (1 - alpha)  - T_final * bg.dL/dC / (1 - alpha);
 //   * 10 totals reduced with a transposed butterfly (12 shuffles), accumulated per tile in shared
 //     memory, flushed with red.global.add.v4/v2.f32 (3 vector reductions per tile instance).
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace dogs {
 
@@ -131,6 +131,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     // rows 0-1 of the tile = the first warp of the reference's 16x16 forward block
     if (k == 0 && (lane >> 3) < 2) lmax01 = max(lmax01, last[k]);
   }
+  const float rx0 = (float)(blockIdx.x * TILE_X + 8 * warp), ry0 = (float)(blockIdx.y * TILE_Y);
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
 
@@ -182,7 +183,27 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int nbatch = min(BB_BATCH, (int)todo_total - i * BB_BATCH);
     const uint32_t base = i * BB_BATCH;
 
-    for (int j = 0; j < nbatch; j++) {
+    // Sub-tile culling (blend_common.cuh): which entries of the batch can reach this warp's 8x16
+    // half tile at all; one entry per lane and round.
+    uint32_t hm[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const int jj = 32 * w + lane;
+      bool h = false;
+      if (jj < nbatch) {
+        const float4 bb = sB[buf][jj];
+        h = block_reachable(sA[buf][jj], bb.x, bb.y, rx0, ry0, rx0 + 7.f, ry0 + 15.f, sC[buf][jj].w);
+      }
+      hm[w] = __ballot_sync(0xffffffffu, h);
+    }
+
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+    uint32_t m = hm[w];
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      const int j = 32 * w + bit;
       const uint32_t e = base + j;
       const float4 con_o = sA[buf][j];
       const float4 b = sB[buf][j];
@@ -236,6 +257,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       }
       const float tot = bb_warp_reduce10(v, lane);
       if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
+    }
     }
     __syncthreads();
     // flush the batch: thread t owns splat t

@@ -1,0 +1,144 @@
+// blend_fwd_kernel — per-tile front-to-back alpha blend (replaces renderCUDA,
+// cuda_rasterizer/forward.cu:349-501).  The per-pixel arithmetic (power, expf, alpha clamp, the
+// 1/255 and 1e-4 thresholds, colour / inverse-depth accumulation) is the reference's, expression
+// for expression, so n_contrib, final_T and the image are bit-identical.
+//
+// What differs:
+//   * one CTA (256 threads) per 16x16 tile, but each warp owns a compact 8x4 pixel block and, per
+//     staged batch, first culls the list against its own block with one entry per lane
+//     (block_reachable, blend_common.cuh); the per-pixel loop only visits the surviving entries.
+//     ncu of the first version showed the kernel instruction-issue bound (91 % issue-active) with
+//     every pixel testing every list entry;
+//   * batches of 256 records are gathered global->shared with cp.async into a double buffer, so
+//     the gather of batch i+1 overlaps the blend of batch i (the reference loads colour and depth
+//     from global memory inside the inner loop, forward.cu:471,473);
+//   * no per-bucket (T, colour, depth) snapshots are written: the backward replays the blend from
+//     final_T / n_contrib (blend_bwd.cu).
+#include "blend_common.cuh"
+
+namespace dogs {
+
+__global__ void __launch_bounds__(TILE_PIX)
+blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
+                 int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
+                 float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                 float* __restrict__ out_color, float* __restrict__ invdepth,
+                 float* __restrict__ pix_color, float* __restrict__ pix_invdepth) {
+  __shared__ float4 sA[2][TILE_PIX];
+  __shared__ float4 sB[2][TILE_PIX];
+  __shared__ float4 sC[2][TILE_PIX];
+  const uint32_t tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+  // warp -> 8x4 block (2 columns x 4 rows of blocks per tile); lane -> pixel inside the block
+  const uint32_t bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
+  const uint2 pix = {bx0 + (lane & 7), by0 + (lane >> 3)};
+  const uint32_t pix_id = W * pix.y + pix.x;
+  const float2 pixf = {(float)pix.x, (float)pix.y};
+  const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
+  bool done = !inside;
+  const float rx0 = (float)bx0, ry0 = (float)by0, rx1 = (float)(bx0 + 7), ry1 = (float)(by0 + 3);
+
+  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+  const int rounds = ((range.y - range.x + TILE_PIX - 1) / TILE_PIX);
+  int toDo = range.y - range.x;
+
+  float T = 1.0f;
+  uint32_t last_contributor = 0;
+  float C[3] = {0.f, 0.f, 0.f};
+  float expected_invdepth = 0.0f;
+
+  auto fetch = [&](int round, int buf) {
+    uint32_t progress = range.x + round * TILE_PIX + tid;
+    if (progress < range.y) {
+      const SplatRecord* r = rec + point_list[progress];
+      cp_async16(&sA[buf][tid], &r->a);
+      cp_async16(&sB[buf][tid], &r->b);
+      cp_async16(&sC[buf][tid], &r->c);
+    }
+    cp_async_commit();
+  };
+  if (rounds > 0) fetch(0, 0);
+
+  for (int i = 0; i < rounds; i++, toDo -= TILE_PIX) {
+    const int buf = i & 1;
+    // forward.cu:415-417 (the barrier also frees buffer buf^1, last read in round i-1)
+    int num_done = __syncthreads_count(done);
+    if (num_done == TILE_PIX) break;
+    if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int nbatch = min(TILE_PIX, toDo);
+    const uint32_t base = i * TILE_PIX;
+
+    // which entries of the batch can reach this warp's 8x4 block (one entry per lane)
+    uint32_t hit[TILE_PIX / 32];
+#pragma unroll
+    for (int r = 0; r < TILE_PIX / 32; r++) {
+      const int j = r * 32 + lane;
+      bool h = false;
+      if (j < nbatch) {
+        const float4 b = sB[buf][j];
+        h = block_reachable(sA[buf][j], b.x, b.y, rx0, ry0, rx1, ry1, sC[buf][j].w);
+      }
+      hit[r] = __ballot_sync(0xffffffffu, h);
+    }
+
+#pragma unroll
+    for (int r = 0; r < TILE_PIX / 32; r++) {
+      uint32_t m = hit[r];
+      while (m) {
+        if (__all_sync(0xffffffffu, done)) { m = 0; break; }
+        const int j = r * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (done) continue;
+        const float4 con_o = sA[buf][j];
+        const float4 b = sB[buf][j];
+        float2 xy = {b.x, b.y};
+        float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+        float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+        if (power > 0.0f) continue;
+        float alpha = min(0.99f, con_o.w * exp(power));
+        if (alpha < 1.0f / 255.0f) continue;
+        float test_T = T * (1 - alpha);
+        if (test_T < 0.0001f) {
+          done = true;
+          continue;
+        }
+        const float4 c = sC[buf][j];
+        C[0] += b.w * alpha * T;
+        C[1] += c.x * alpha * T;
+        C[2] += c.y * alpha * T;
+        expected_invdepth += b.z * alpha * T;
+        T = test_T;
+        last_contributor = base + j + 1;   // forward.cu:444,479: position in the tile's list
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  if (inside) {
+    final_T[pix_id] = T;
+    n_contrib[pix_id] = last_contributor;
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      const float v = C[ch] + T * bg_color[ch];
+      out_color[ch * HW + pix_id] = v;
+      pix_color[ch * HW + pix_id] = v;  // rasterizer_impl.cu:495-496 (copy kept for backward)
+    }
+    invdepth[pix_id] = expected_invdepth;
+    pix_invdepth[pix_id] = expected_invdepth;
+  }
+}
+
+int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
+                     float* out_color, float* out_invdepth, cudaStream_t s) {
+  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
+  blend_fwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+                                             im.final_T, im.n_contrib, out_color, out_invdepth,
+                                             im.pix_color, im.pix_invdepth);
+  return check_launch("blend_fwd", prm.debug != 0, s);
+}
+
+}  // namespace dogs

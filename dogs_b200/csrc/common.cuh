@@ -144,7 +144,7 @@ __device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mea
 }
 
 // Internal per-Gaussian record written by preprocess and gathered by the blend kernels.
-// a = {conic.x, conic.y, conic.z, opacity}, b = {x, y, 1/depth, r}, c = {g, b, depth, unused}
+// a = {conic.x, conic.y, conic.z, opacity}, b = {x, y, 1/depth, r}, c = {g, b, depth, ln(255*opacity)}
 struct __align__(16) SplatRecord { float4 a, b, c; };
 
 // ---- stage launchers (defined in the .cu files) -----------------------------------

@@ -194,11 +194,11 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     SplatRecord r;
     r.a = co;
     r.b = {point_image.x, point_image.y, 1.f / depth, rgb.x};
-    r.c = {rgb.y, rgb.z, depth, 0.f};
-    rec[idx] = r;
-
     // rasterizer_impl.cu:151-177: count the tiles of the rect the Gaussian can actually reach.
     const float thr = logf(co.w / (1.0f / 255.0f));
+    r.c = {rgb.y, rgb.z, depth, thr};
+    rec[idx] = r;
+
     const int rw = rect_max.x - rect_min.x;
     const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64;   // mask of reachable tiles fits 64 bits
     for (int y = rect_min.y; y < (int)rect_max.y; y++)
@@ -276,108 +276,6 @@ tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys, uint2* __
     }
   }
   if (idx == L - 1) ranges[cur].y = L;
-}
-
-// ---- blend ------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
-// One CTA per 16x16 tile, one thread per pixel (renderCUDA, forward.cu:349-501).  Batches of 256
-// records are gathered global->shared with cp.async into a double buffer, so the gather of batch
-// i+1 overlaps the blend of batch i.  No per-bucket state is written: the backward replays the
-// blend front to back from final_T / n_contrib (see rasterizer_bwd.cu).
-__global__ void __launch_bounds__(TILE_PIX)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
-                 int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
-                 float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                 float* __restrict__ out_color, float* __restrict__ invdepth,
-                 float* __restrict__ pix_color, float* __restrict__ pix_invdepth) {
-  __shared__ float4 sA[2][TILE_PIX];
-  __shared__ float4 sB[2][TILE_PIX];
-  __shared__ float4 sC[2][TILE_PIX];
-  const uint32_t tid = threadIdx.y * TILE_X + threadIdx.x;
-  const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-  const uint2 pix = {blockIdx.x * TILE_X + threadIdx.x, blockIdx.y * TILE_Y + threadIdx.y};
-  const uint32_t pix_id = W * pix.y + pix.x;
-  const float2 pixf = {(float)pix.x, (float)pix.y};
-  const bool inside = pix.x < (uint32_t)W && pix.y < (uint32_t)H;
-  bool done = !inside;
-
-  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
-  const int rounds = ((range.y - range.x + TILE_PIX - 1) / TILE_PIX);
-  int toDo = range.y - range.x;
-
-  float T = 1.0f;
-  uint32_t contributor = 0, last_contributor = 0;
-  float C[3] = {0.f, 0.f, 0.f};
-  float expected_invdepth = 0.0f;
-
-  auto fetch = [&](int round, int buf) {
-    uint32_t progress = range.x + round * TILE_PIX + tid;
-    if (progress < range.y) {
-      const SplatRecord* r = rec + point_list[progress];
-      cp_async16(&sA[buf][tid], &r->a);
-      cp_async16(&sB[buf][tid], &r->b);
-      cp_async16(&sC[buf][tid], &r->c);
-    }
-    cp_async_commit();
-  };
-  if (rounds > 0) fetch(0, 0);
-
-  for (int i = 0; i < rounds; i++, toDo -= TILE_PIX) {
-    const int buf = i & 1;
-    // forward.cu:415-417 (the barrier also frees buffer buf^1, last read in round i-1)
-    int num_done = __syncthreads_count(done);
-    if (num_done == TILE_PIX) break;
-    if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    for (int j = 0; !done && j < min(TILE_PIX, toDo); j++) {
-      contributor++;
-      const float4 con_o = sA[buf][j];
-      const float4 b = sB[buf][j];
-      float2 xy = {b.x, b.y};
-      float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-      float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-      if (power > 0.0f) continue;
-      float alpha = min(0.99f, con_o.w * exp(power));
-      if (alpha < 1.0f / 255.0f) continue;
-      float test_T = T * (1 - alpha);
-      if (test_T < 0.0001f) {
-        done = true;
-        continue;
-      }
-      const float4 c = sC[buf][j];
-      C[0] += b.w * alpha * T;
-      C[1] += c.x * alpha * T;
-      C[2] += c.y * alpha * T;
-      expected_invdepth += b.z * alpha * T;
-      T = test_T;
-      last_contributor = contributor;
-    }
-  }
-  cp_async_wait<0>();
-
-  if (inside) {
-    final_T[pix_id] = T;
-    n_contrib[pix_id] = last_contributor;
-    const size_t HW = (size_t)H * W;
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-      const float v = C[ch] + T * bg_color[ch];
-      out_color[ch * HW + pix_id] = v;
-      pix_color[ch * HW + pix_id] = v;  // rasterizer_impl.cu:495-496 (copy kept for backward)
-    }
-    invdepth[pix_id] = expected_invdepth;
-    pix_invdepth[pix_id] = expected_invdepth;
-  }
 }
 
 // ---- visible_filter / mark_visible ---------------------------------------------------
@@ -483,16 +381,6 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_ke
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
   if (R > 0) tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, ranges);
   return check_launch("tile_ranges", prm.debug != 0, s);
-}
-
-int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
-                     float* out_color, float* out_invdepth, cudaStream_t s) {
-  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
-  dim3 block(TILE_X, TILE_Y, 1);
-  blend_fwd_kernel<<<grid, block, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
-                                          im.final_T, im.n_contrib, out_color, out_invdepth,
-                                          im.pix_color, im.pix_invdepth);
-  return check_launch("blend_fwd", prm.debug != 0, s);
 }
 
 int launch_filter(const DgrParams& prm, const float* means3D, const float* scales,
