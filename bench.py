@@ -270,14 +270,18 @@ def main():
         marks = [ev0]
         for it in range(K):
             step(sc, target)
-            if not args.no_clocks and it in (K // 3, (2 * K) // 3):
-                clk.sample()                          # clocks / throttle reasons under load
             m = torch.cuda.Event(enable_timing=True)
             m.record()
             marks.append(m)
         if admm is not None:
             admm.consensus()
         ev1.record()
+        # Clocks / throttle reasons under load: the host has enqueued the whole region, the GPU is
+        # still executing its tail (ev1 not reached yet).  Querying NVML between launches instead was
+        # measured to stall the launching thread for 10-25 ms per query.
+        if not args.no_clocks:
+            for _ in range(3):
+                clk.sample()
         barrier()
     ms = ev0.elapsed_time(ev1)
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
@@ -296,18 +300,54 @@ def main():
         host_cam = {k: sc[k].cpu().pin_memory() for k in ("viewmatrix", "projmatrix", "campos")}
         h2d = host_target.numel() * 4 + sum(v.numel() * 4 for v in host_cam.values())
 
-        def e2e_step():
-            scene = dict(sc)
-            for k, v in host_cam.items():
-                scene[k] = v.to(dev, non_blocking=True)
-            tgt = host_target.to(dev, non_blocking=True)
-            return float(step(scene, tgt).item())   # .item(): D2H read of the loss (4 B)
-        for _ in range(3):
-            e2e_step()
+        # Per-step host inputs are double-buffered on a copy stream (the H2D copy of step i+1 overlaps the
+        # compute of step i) and the loss is read back with a one-step lag through pinned memory, the way
+        # an asynchronous data loader / logger drives a trainer.  Every step still copies its own target
+        # image + camera H2D and its own loss D2H inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        dev_target = [torch.empty_like(target) for _ in range(2)]
+        dev_cam = [{k: torch.empty_like(sc[k]) for k in host_cam} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+        losses = []
+
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])           # the step that last used buffer b is finished
+                dev_target[b].copy_(host_target, non_blocking=True)
+                for k, v in host_cam.items():
+                    dev_cam[b][k].copy_(v, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream(dev)
+            for b in range(2):
+                consumed[b].record(cur)
+            prefetch(0)
+            for i in range(n):
+                b = i % 2
+                if i + 1 < n:
+                    prefetch(i + 1)
+                cur.wait_event(ready[b])
+                scene = dict(sc)
+                scene.update(dev_cam[b])
+                loss = step(scene, dev_target[b])
+                consumed[b].record(cur)
+                loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of this step's loss (4 B)
+                loss_ev[b].record(cur)
+                if i >= 1:                                     # read the previous step's loss on the host
+                    loss_ev[1 - b].synchronize()
+                    losses.append(float(loss_host[1 - b][0]))
+            loss_ev[(n - 1) % 2].synchronize()
+            losses.append(float(loss_host[(n - 1) % 2][0]))
+
+        e2e_loop(3)
         barrier()
         ev0.record()
-        for _ in range(K):
-            e2e_step()
+        e2e_loop(K)
         if admm is not None:
             admm.consensus()
         ev1.record()

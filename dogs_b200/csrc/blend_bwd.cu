@@ -236,7 +236,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float Tk = T[k];
         const float weight = alpha * Tk;
         const float om = 1.0f - alpha;
-        const float inv = __frcp_rn(om);
+        const float inv = __fdividef(1.0f, om);   // MUFU.RCP (<= 1 ulp): gradients carry a 1e-4 bar
         S[k] += weight * cd;
         const float dL_dalpha = c[k] ? (cd * Tk + inv * (S[k] - bgT[k])) : 0.f;
         T[k] = Tk * om;

@@ -153,7 +153,7 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, V3 pos, V3 campos, uin
 
 constexpr int PREB_THREADS = 128;
 
-__global__ void __launch_bounds__(PREB_THREADS)
+__global__ void __launch_bounds__(PREB_THREADS, 5)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ dc,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
