@@ -63,7 +63,7 @@ SIGNATURES = {
     "fssim_backward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 7 + [_P],
     "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],
     "admm_pack": [C.POINTER(AdmmTensors), _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P],
-    "admm_unpack_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, C.c_int64, _P, C.c_float, _P, _P],
+    "admm_unpack_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, _P, C.c_int64, _P, C.c_float, _P, _P],
     "admm_penalty": [C.POINTER(AdmmTensors)] * 3 + [_P, C.c_int64, _P, _P, _P],
     "dogs_last_error": [],
     "dogs_abi_version": [],

@@ -90,22 +90,25 @@ class CudaOps:
                                             plan.S, plan.S_total, 1, sendbuf.data_ptr(),
                                             self.L.stream_ptr(dev)))
 
-    def unpack_update(self, x, u, z, plan, recvbuf, relax, residuals):
+    def unpack_update(self, x, u, z, plan, recvbuf, relax, residuals, zmu=None):
         xs, us, zs = self._t6(x), self._t6(u), self._t6(z)
+        zm = self._t6(zmu) if zmu is not None else None
         dev = residuals.device
         with torch.cuda.device(dev):
             self.L.check(self.lib.admm_unpack_update(
-                C.byref(xs), C.byref(us), C.byref(zs), plan.slot_of_local.data_ptr(),
+                C.byref(xs), C.byref(us), C.byref(zs), C.byref(zm) if zm is not None else None,
+                plan.slot_of_local.data_ptr(),
                 plan.inv_count.data_ptr(), plan.n_local, recvbuf.data_ptr() if recvbuf.numel() else None,
                 float(relax), residuals.data_ptr(), self.L.stream_ptr(dev)))
 
     def penalty(self, x, u, z, grads, n, coef, sums):
-        xs, us, zs = self._t6(x), self._t6(u), self._t6(z)
+        xs, zs = self._t6(x), self._t6(z)
+        us = self._t6(u) if u is not None else None
         gs = self._t6(grads) if grads is not None else None
         carr = (C.c_float * 6)(*[float(c) for c in coef])
         dev = sums.device
         with torch.cuda.device(dev):
-            self.L.check(self.lib.admm_penalty(C.byref(xs), C.byref(us), C.byref(zs),
+            self.L.check(self.lib.admm_penalty(C.byref(xs), C.byref(us) if us is not None else None, C.byref(zs),
                                                C.byref(gs) if gs is not None else None, n, carr,
                                                sums.data_ptr(), self.L.stream_ptr(dev)))
 
@@ -130,6 +133,9 @@ class AdmmBlock:
         # setup_dual_variables (slave:81-97): u := 0;  z := x (set_global_gaussians after fusion)
         self.u = [torch.zeros_like(t) for t in self.x]
         self.z = [t.detach().clone() for t in self.x]
+        # zmu = z - u, refreshed by every consensus round: the per-iteration penalty then reads one
+        # tensor set instead of two (r = x - zmu)
+        self.zmu = [t.detach().clone() for t in self.x]
         # setup_penalty_parameters (master:326-334): rho_g = alpha_g / N_global
         self.rho = [a / plan.n_global for a in alphas]
         self.relax = 1.0 + over_relaxation_coeff
@@ -153,7 +159,7 @@ class AdmmBlock:
         if self._world() > 1 and self.plan.S_total > 0:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
         self.residuals.zero_()
-        self.ops.unpack_update(x, self.u, self.z, self.plan, self.buf, self.relax, self.residuals)
+        self.ops.unpack_update(x, self.u, self.z, self.plan, self.buf, self.relax, self.residuals, self.zmu)
         res = self.residuals.clone()
         # primal_g = sum_k mse(z[idx_k], x_k): every block divides by its own element count
         n = self.plan.n_local
@@ -184,7 +190,7 @@ class AdmmBlock:
             if t.grad is None:
                 t.grad = torch.zeros_like(t)
         self.pen_sums.zero_()
-        self.ops.penalty([t.detach() for t in self.x], self.u, self.z, [t.grad for t in self.x], n, coef,
+        self.ops.penalty([t.detach() for t in self.x], None, self.zmu, [t.grad for t in self.x], n, coef,
                          self.pen_sums)
         scale = torch.tensor([0.5 * c for c in coef], dtype=torch.float64, device=self.pen_sums.device)
         return self.pen_sums * scale

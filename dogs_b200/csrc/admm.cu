@@ -60,7 +60,7 @@ admm_penalty_kernel(const __grid_constant__ PenaltyArgs a, double* __restrict__ 
     float s = 0.f;
     if (e0 + 4 <= a.len[g]) {
       const float4 xv = *reinterpret_cast<const float4*>(xp + e0);
-      const float4 uv = *reinterpret_cast<const float4*>(up + e0);
+      const float4 uv = up ? *reinterpret_cast<const float4*>(up + e0) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 zv = *reinterpret_cast<const float4*>(zp + e0);
       const float r0 = (xv.x + uv.x) - zv.x, r1 = (xv.y + uv.y) - zv.y;   // mse_loss(x + u, z), slave:169-187
       const float r2 = (xv.z + uv.z) - zv.z, r3 = (xv.w + uv.w) - zv.w;
@@ -72,7 +72,7 @@ admm_penalty_kernel(const __grid_constant__ PenaltyArgs a, double* __restrict__ 
       }
     } else {
       for (unsigned long long e = e0; e < a.len[g]; e++) {
-        const float r = (xp[e] + up[e]) - zp[e];
+        const float r = (xp[e] + (up ? up[e] : 0.f)) - zp[e];
         s += r * r;
         if (gp) gp[e] += coef * r;
       }
@@ -110,7 +110,7 @@ admm_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ local_
 template <int SZ>
 __global__ void __launch_bounds__(ADMM_THREADS)
 admm_unpack_kernel(const float* __restrict__ x, float* __restrict__ u, float* __restrict__ z,
-                   const int64_t* __restrict__ slot_of_local, const float* __restrict__ inv_count,
+                   float* __restrict__ zmu, const int64_t* __restrict__ slot_of_local, const float* __restrict__ inv_count,
                    unsigned long long total, int start, const float* __restrict__ recvbuf, float relax,
                    double* __restrict__ residuals, int g) {
   __shared__ double acc[2];
@@ -128,7 +128,9 @@ admm_unpack_kernel(const float* __restrict__ x, float* __restrict__ u, float* __
     if (sl >= 0) {
       const float w = inv_count[i];
       z_new = recvbuf[sl * ADMM_ROW + start + off] * w;
-      u[e] += relax * (xv - z_new);
+      const float u_new = u[e] + relax * (xv - z_new);
+      u[e] = u_new;
+      if (zmu) zmu[e] = z_new - u_new;
       const float dp = z_new - xv;
       primal += (double)dp * dp;
       const float dd = z_old - z_new;
@@ -137,6 +139,7 @@ admm_unpack_kernel(const float* __restrict__ x, float* __restrict__ u, float* __
       z_new = xv;
       const float dd = z_old - z_new;
       dual += (double)dd * dd;
+      if (zmu) zmu[e] = z_new - u[e];
     }
     z[e] = z_new;
   }
@@ -178,14 +181,14 @@ extern "C" int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, co
 }
 
 extern "C" int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
-                                  const int64_t* slot_of_local, const float* inv_count, int64_t n,
+                                  const AdmmTensors* zmu, const int64_t* slot_of_local, const float* inv_count, int64_t n,
                                   const float* recvbuf, float relax, double* residuals, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
   if (!x || !u || !z || !slot_of_local || !inv_count || !residuals) { set_error("admm_unpack_update: null pointer"); return 1; }
 #define UNPACK(G, SZ)                                                                                 \
   admm_unpack_kernel<SZ><<<grid_for((unsigned long long)n * SZ), ADMM_THREADS, 0, s>>>(               \
-      x->g[G], u->g[G], z->g[G], slot_of_local, inv_count, (unsigned long long)n * SZ, kStart[G], recvbuf, \
+      x->g[G], u->g[G], z->g[G], zmu ? zmu->g[G] : nullptr, slot_of_local, inv_count, (unsigned long long)n * SZ, kStart[G], recvbuf, \
       relax, residuals, G)
   UNPACK(0, 3); UNPACK(1, 3); UNPACK(2, 45); UNPACK(3, 3); UNPACK(4, 4); UNPACK(5, 1);
 #undef UNPACK
@@ -197,11 +200,11 @@ extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u
                             void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
-  if (!x || !u || !z || !coef || !sums) { set_error("admm_penalty: null pointer"); return 1; }
+  if (!x || !z || !coef || !sums) { set_error("admm_penalty: null pointer"); return 1; }
   PenaltyArgs a;
   unsigned long long end = 0;
   for (int g = 0; g < 6; g++) {
-    a.x[g] = x->g[g]; a.u[g] = u->g[g]; a.z[g] = z->g[g];
+    a.x[g] = x->g[g]; a.u[g] = u ? u->g[g] : nullptr; a.z[g] = z->g[g];
     a.grad[g] = grad ? grad->g[g] : nullptr;
     a.len[g] = (unsigned long long)n * kSize[g];
     end += (a.len[g] + 3) / 4;

@@ -172,9 +172,11 @@ int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, const int64_t
  * residuals (device double[12]) is ACCUMULATED: [0..5] sum((z-x)^2) per group (primal, master:396-432),
  * [6..11] sum(inv_count*(z_prev-z)^2) per group (dual, master:435-456; each global Gaussian once). */
 int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
+                       const AdmmTensors* zmu /* nullable: receives z - u for the penalty fast path */,
                        const int64_t* slot_of_local, const float* inv_count, int64_t n,
                        const float* recvbuf, float relax, double* residuals, void* stream);
-/* penalty (slave:161-202): sums[g] += sum((x_g+u_g-z_g)^2) (device double[6]); if grad != NULL,
+/* penalty (slave:161-202): sums[g] += sum((x_g+u_g-z_g)^2) (device double[6]); u == NULL means that
+ * `z` already holds z - u (the zmu tensors of admm_unpack_update: one pass less per iteration); if grad != NULL,
  * grad_g += coef[g]*(x_g+u_g-z_g) with coef[g] = rho_g/numel_g (host float[6]) — the gradient of
  * 0.5*rho_g*mse_loss(x_g+u_g, z_g). */
 int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u, const AdmmConstTensors* z,

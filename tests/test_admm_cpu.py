@@ -25,7 +25,7 @@ class OracleOps:
             buf[plan.slot, off:off + sz] = x[g].view(plan.n_local, sz)[plan.local_idx]
             off += sz
 
-    def unpack_update(self, x, u, z, plan, recvbuf, relax, residuals):
+    def unpack_update(self, x, u, z, plan, recvbuf, relax, residuals, zmu=None):
         buf = recvbuf.view(-1, A.ROW)
         off = 0
         shared = plan.slot_of_local >= 0
@@ -37,11 +37,13 @@ class OracleOps:
             residuals[g] += ((z_new - xg).double() ** 2).sum()
             residuals[6 + g] += (plan.inv_count[:, None].double() * (zg - z_new).double() ** 2).sum()
             zg.copy_(z_new)
+            if zmu is not None:
+                zmu[g].view(plan.n_local, sz).copy_(z_new - ug)
             off += sz
 
     def penalty(self, x, u, z, grads, n, coef, sums):
         for g in range(6):
-            r = (x[g] + u[g]) - z[g]
+            r = (x[g] + u[g]) - z[g] if u is not None else x[g] - z[g]
             sums[g] += (r.double() ** 2).sum()
             if grads is not None:
                 grads[g] += coef[g] * r

@@ -156,7 +156,7 @@ def test_admm_consensus_kernels_vs_oracle():
     dual = np.zeros(6)
     for b in blocks:
         b.residuals.zero_()
-        b.ops.unpack_update(b.x, b.u, b.z, b.plan, total, b.relax, b.residuals)
+        b.ops.unpack_update(b.x, b.u, b.z, b.plan, total, b.relax, b.residuals, b.zmu)
         r = b.residuals.cpu().numpy()
         prim += r[:6] / (b.plan.n_local * np.array(O.GROUP_SIZES))
         dual += r[6:]
