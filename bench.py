@@ -230,6 +230,7 @@ def main():
         plan = A.build_plan(gidx.to(dev), n_global).to(dev)
         x = [leaves[k] for k in ("means3D", "dc", "sh", "scales", "rotations", "opacities")]
         admm = A.AdmmBlock(x, plan)                  # penalty gradients accumulate into the leaves' .grad
+        admm.fuse_into_rasterizer(True)              # xyz / f_dc / f_rest penalty fused into the rasterizer backward
 
     def loss_of(img, tgt):
         l1 = (img - tgt).abs().mean()

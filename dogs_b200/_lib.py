@@ -14,6 +14,12 @@ LIB_PATH = os.path.join(_HERE, "libdogs_b200.so")
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 
+class DgrAdmmPenalty(C.Structure):
+    _fields_ = [("zmu_xyz", C.c_void_p), ("zmu_dc", C.c_void_p), ("zmu_sh", C.c_void_p),
+                ("coef_xyz", C.c_float), ("coef_dc", C.c_float), ("coef_sh", C.c_float),
+                ("sums", C.c_void_p)]
+
+
 class DgrParams(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("D", C.c_int32), ("M", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
@@ -23,6 +29,7 @@ class DgrParams(C.Structure):
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
         ("campos", C.c_void_p),
         ("ref_bucket_cull_quirk", C.c_int32),
+        ("admm", C.POINTER(DgrAdmmPenalty)),
     ]
 
 

@@ -77,6 +77,9 @@ class CudaOps:
     def _t6(self, ts):
         arr = self.L.AdmmTensors()
         for i, t in enumerate(ts):
+            if t is None:            # group handled elsewhere (fused into the rasterizer backward)
+                arr.g[i] = None
+                continue
             if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError("ADMM tensors must be contiguous float32 CUDA tensors")
             arr.g[i] = t.data_ptr()
@@ -143,6 +146,8 @@ class AdmmBlock:
         self.buf = torch.zeros(max(plan.S_total, 1) * ROW, dtype=torch.float32, device=dev)
         self.residuals = torch.zeros(12, dtype=torch.float64, device=dev)
         self.pen_sums = torch.zeros(6, dtype=torch.float64, device=dev)
+        self.fused_sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.fused = False
         self.last_primal: Optional[List[float]] = None
         self.last_dual: Optional[List[float]] = None
 
@@ -179,6 +184,20 @@ class AdmmBlock:
                     self.rho[g] /= self.tau_dec
         return primal, dual
 
+    def fused_coef(self):
+        n = self.plan.n_local
+        return [self.rho[g] / max(n * GROUP_SIZES[g], 1) for g in range(3)]
+
+    def fuse_into_rasterizer(self, enable: bool = True):
+        """Let the rasterizer backward add the penalty gradient of xyz / f_dc / f_rest (51 of the 59
+        floats) while it writes those gradients anyway (DgrAdmmPenalty); add_penalty_grads_ then only
+        touches scaling / quaternion / opacity.  Valid when the rasterizer is fed this block's raw
+        xyz, f_dc and f_rest tensors (conerf's render() does)."""
+        from . import diff_gaussian_rasterization as dgr
+        self.fused = bool(enable)
+        dgr.set_fused_admm(self if enable else None)
+        self.fused_sums.zero_()
+
     @torch.no_grad()
     def add_penalty_grads_(self):
         """add_admm_penalties (slave:161-202) fused with its own backward: accumulates
@@ -190,8 +209,13 @@ class AdmmBlock:
             if t.grad is None:
                 t.grad = torch.zeros_like(t)
         self.pen_sums.zero_()
-        self.ops.penalty([t.detach() for t in self.x], None, self.zmu, [t.grad for t in self.x], n, coef,
-                         self.pen_sums)
+        xs = [t.detach() for t in self.x]
+        if self.fused:   # groups 0-2 were handled by the rasterizer backward of this iteration
+            xs = [None, None, None] + xs[3:]
+        self.ops.penalty(xs, None, self.zmu, [t.grad for t in self.x], n, coef, self.pen_sums)
+        if self.fused:
+            self.pen_sums[:3] += self.fused_sums
+            self.fused_sums.zero_()
         scale = torch.tensor([0.5 * c for c in coef], dtype=torch.float64, device=self.pen_sums.device)
         return self.pen_sums * scale
 

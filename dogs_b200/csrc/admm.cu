@@ -206,7 +206,7 @@ extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u
   for (int g = 0; g < 6; g++) {
     a.x[g] = x->g[g]; a.u[g] = u ? u->g[g] : nullptr; a.z[g] = z->g[g];
     a.grad[g] = grad ? grad->g[g] : nullptr;
-    a.len[g] = (unsigned long long)n * kSize[g];
+    a.len[g] = a.x[g] ? (unsigned long long)n * kSize[g] : 0ull;   // NULL x tensor: group handled elsewhere
     end += (a.len[g] + 3) / 4;
     a.chunk_end[g] = end;
     a.coef[g] = coef[g];

@@ -13,6 +13,7 @@
 // (backward.cu:398-451) and writes every output gradient exactly once (zeros for culled
 // Gaussians), which removes the 308 B/Gaussian of torch::zeros memsets
 // (rasterize_points.cu:196-207).
+#include <string.h>
 #include "common.cuh"
 
 namespace dogs {
@@ -167,7 +168,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       float* __restrict__ dL_ddc, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dcolors_precomp, float* __restrict__ dL_dopacity_out,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drots,
-                      float* __restrict__ dL_dcov3D_out) {
+                      float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm) {
   extern __shared__ float4 stage4[];
   float* stage = reinterpret_cast<float*>(stage4);
   const int first = blockIdx.x * PREB_THREADS;
@@ -190,6 +191,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     __syncthreads();
   }
 
+  double pen_xyz = 0.0, pen_dc = 0.0, pen_sh = 0.0;
   if (idx < P) {
     float* sh_row = stage + (size_t)threadIdx.x * 3 * M;
     float3 g_mean3D = {0.f, 0.f, 0.f};
@@ -382,6 +384,22 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         g_mean2D.y *= sf;
       }
     }
+    if (admm.zmu_xyz) {
+      // Fused ADMM penalty (slave_gaussian_trainer.py:161-202) on the consensus variables that are
+      // direct rasterizer inputs: grad += rho_g/numel_g * (x - (z - u)), for EVERY Gaussian of the block.
+      const float r0 = means3D[3 * idx] - admm.zmu_xyz[3 * idx];
+      const float r1 = means3D[3 * idx + 1] - admm.zmu_xyz[3 * idx + 1];
+      const float r2 = means3D[3 * idx + 2] - admm.zmu_xyz[3 * idx + 2];
+      g_mean3D.x += admm.coef_xyz * r0; g_mean3D.y += admm.coef_xyz * r1; g_mean3D.z += admm.coef_xyz * r2;
+      pen_xyz = (double)(r0 * r0 + r1 * r1 + r2 * r2);
+      if (dL_ddc && admm.zmu_dc) {
+        const float q0 = dc[3 * idx] - admm.zmu_dc[3 * idx];
+        const float q1 = dc[3 * idx + 1] - admm.zmu_dc[3 * idx + 1];
+        const float q2 = dc[3 * idx + 2] - admm.zmu_dc[3 * idx + 2];
+        g_dc.x += admm.coef_dc * q0; g_dc.y += admm.coef_dc * q1; g_dc.z += admm.coef_dc * q2;
+        pen_dc = (double)(q0 * q0 + q1 * q1 + q2 * q2);
+      }
+    }
     dL_dmeans3D[3 * idx] = g_mean3D.x; dL_dmeans3D[3 * idx + 1] = g_mean3D.y; dL_dmeans3D[3 * idx + 2] = g_mean3D.z;
     dL_dmeans2D[3 * idx] = g_mean2D.x; dL_dmeans2D[3 * idx + 1] = g_mean2D.y; dL_dmeans2D[3 * idx + 2] = 0.f;
     dL_dopacity_out[idx] = g_opacity;
@@ -400,13 +418,48 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   if (sh_path) {
     __syncthreads();
     float* dst = dL_dsh + (size_t)first * 3 * M;
-    if ((((uintptr_t)dst) & 15) == 0) {
+    const bool pen = admm.zmu_sh != nullptr;
+    const float* xs = shs + (size_t)first * 3 * M;            // still L2-resident: this CTA just read it
+    const float* zs = pen ? admm.zmu_sh + (size_t)first * 3 * M : nullptr;
+    const bool al16 = ((((uintptr_t)dst) | ((uintptr_t)xs) | ((uintptr_t)zs)) & 15) == 0;
+    if (al16) {
       float4* dst4 = reinterpret_cast<float4*>(dst);
       const size_t n4 = nfl >> 2;
-      for (size_t i = threadIdx.x; i < n4; i += PREB_THREADS) dst4[i] = stage4[i];
-      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) dst[i] = stage[i];
+      for (size_t i = threadIdx.x; i < n4; i += PREB_THREADS) {
+        float4 g = stage4[i];
+        if (pen) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xs) + i);
+          const float4 zv = __ldg(reinterpret_cast<const float4*>(zs) + i);
+          const float r0 = xv.x - zv.x, r1 = xv.y - zv.y, r2 = xv.z - zv.z, r3 = xv.w - zv.w;
+          g.x += admm.coef_sh * r0; g.y += admm.coef_sh * r1; g.z += admm.coef_sh * r2; g.w += admm.coef_sh * r3;
+          pen_sh += (double)(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+        }
+        dst4[i] = g;
+      }
+      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) {
+        float g = stage[i];
+        if (pen) { const float r = xs[i] - zs[i]; g += admm.coef_sh * r; pen_sh += (double)(r * r); }
+        dst[i] = g;
+      }
     } else {
-      for (size_t i = threadIdx.x; i < nfl; i += PREB_THREADS) dst[i] = stage[i];
+      for (size_t i = threadIdx.x; i < nfl; i += PREB_THREADS) {
+        float g = stage[i];
+        if (pen) { const float r = xs[i] - zs[i]; g += admm.coef_sh * r; pen_sh += (double)(r * r); }
+        dst[i] = g;
+      }
+    }
+  }
+  if (admm.zmu_xyz && admm.sums) {   // penalty sums for logging: one FP64 atomic per warp and group
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pen_xyz += __shfl_xor_sync(0xffffffffu, pen_xyz, o);
+      pen_dc += __shfl_xor_sync(0xffffffffu, pen_dc, o);
+      pen_sh += __shfl_xor_sync(0xffffffffu, pen_sh, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (pen_xyz != 0.0) atomicAdd(&admm.sums[0], pen_xyz);
+      if (pen_dc != 0.0) atomicAdd(&admm.sums[1], pen_dc);
+      if (pen_sh != 0.0) atomicAdd(&admm.sums[2], pen_sh);
     }
   }
 }
@@ -422,6 +475,10 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
   const float focal_y = prm.H / (2.0f * prm.tanfovy);
   const float focal_x = prm.W / (2.0f * prm.tanfovx);
   const bool sh_path = dL_dsh != nullptr && prm.M > 0;
+  DgrAdmmPenalty admm;
+  memset(&admm, 0, sizeof(admm));
+  if (prm.admm) admm = *prm.admm;
+  if (!sh_path) admm.zmu_sh = nullptr;
   size_t smem = sh_path ? (size_t)PREB_THREADS * 3 * prm.M * sizeof(float) + 16 : 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -437,7 +494,7 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
       prm.scale_modifier, cov3D_precomp, prm.viewmatrix, prm.projmatrix, focal_x, focal_y,
       prm.tanfovx, prm.tanfovy, prm.campos, accum, prm.depth_threshold, prm.antialiasing != 0,
       dL_dmeans3D, dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
-      dL_drotations, dL_dcov3D);
+      dL_drotations, dL_dcov3D, admm);
   return check_launch("preprocess_bwd", prm.debug != 0, s);
 }
 

@@ -41,7 +41,20 @@ def cpu_deep_copy_tuple(input_tuple):
     return tuple(i.cpu().clone() if isinstance(i, torch.Tensor) else i for i in input_tuple)
 
 
-def _params(rs, P, M, device):
+# Optional fused ADMM penalty: an object with attributes zmu (list of 6 tensors, groups xyz, f_dc,
+# f_rest first), coef (6 floats) and fused_sums (double[3] device tensor); see dogs_b200.admm.AdmmBlock.
+# When set, the rasterizer backward adds coef_g * (x_g - zmu_g) to the gradients of means3D / dc / sh
+# (include/dogs_b200.h DgrAdmmPenalty).  The rasterizer must then be fed the block's raw xyz / f_dc /
+# f_rest parameters, which is what conerf's render() does (gaussian_render.py:67-110).
+_FUSED_ADMM = None
+
+
+def set_fused_admm(block):
+    global _FUSED_ADMM
+    _FUSED_ADMM = block
+
+
+def _params(rs, P, M, device, backward=False):
     f = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
     keep = (f(rs.bg), f(rs.viewmatrix), f(rs.projmatrix), f(rs.campos))
     prm = L.DgrParams(
@@ -52,6 +65,17 @@ def _params(rs, P, M, device):
         debug=int(bool(rs.debug)),
         bg=keep[0].data_ptr(), viewmatrix=keep[1].data_ptr(), projmatrix=keep[2].data_ptr(),
         campos=keep[3].data_ptr(), ref_bucket_cull_quirk=int(bool(REFERENCE_BACKWARD_QUIRK)))
+    blk = _FUSED_ADMM
+    if backward and blk is not None:
+        zx, zd, zs = blk.zmu[0], blk.zmu[1], blk.zmu[2]
+        if zx.numel() != 3 * P or zd.numel() != 3 * P or (M > 0 and zs.numel() != 3 * M * P):
+            raise RuntimeError("fused ADMM penalty: the block's tensors do not match the rasterized Gaussians")
+        coef = blk.fused_coef()
+        pen = L.DgrAdmmPenalty(zmu_xyz=zx.data_ptr(), zmu_dc=zd.data_ptr(), zmu_sh=zs.data_ptr() if M > 0 else None,
+                               coef_xyz=coef[0], coef_dc=coef[1], coef_sh=coef[2],
+                               sums=blk.fused_sums.data_ptr())
+        prm.admm = C.pointer(pen)
+        keep = keep + (pen,)
     return prm, keep
 
 
@@ -140,7 +164,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_rotations = None if use_cov else new(P, 4)
         grad_cov3Ds_precomp = new(P, 6) if use_cov else None
         if P != 0:
-            prm, keep = _params(rs, P, M, device)
+            prm, keep = _params(rs, P, M, device, backward=True)
             if grad_out_color is None:
                 grad_out_color = torch.zeros((3, prm.H, prm.W), dtype=torch.float32, device=device)
             grad_out_color = grad_out_color.contiguous()

@@ -34,6 +34,19 @@ typedef char* (*dogs_alloc_fn)(void* user, size_t bytes);
 /* ---- rasterizer ----------------------------------------------------------------
  * Replaces CudaRasterizer::Rasterizer::{forward,backward,visible_filter,markVisible}
  * (cuda_rasterizer/rasterizer.h:22-113) and the glue in rasterize_points.cu:54-252. */
+/* Optional fused ADMM penalty (conerf/trainers/slave_gaussian_trainer.py:161-202) for the three
+ * consensus groups that are direct rasterizer inputs (xyz = means3D, f_dc = dc, f_rest = sh): the
+ * backward adds coef_g * (x_g - zmu_g) to dL_dmeans3D / dL_ddc / dL_dsh of EVERY Gaussian, with
+ * zmu = z - u (admm_unpack_update) and coef_g = rho_g / numel_g, in the pass that writes those
+ * gradients anyway.  sums (device double[3], nullable) += sum (x_g - zmu_g)^2 for logging. */
+typedef struct DgrAdmmPenalty {
+  const float* zmu_xyz;    /* [P,3]   NULL disables the whole fusion */
+  const float* zmu_dc;     /* [P,3]   nullable */
+  const float* zmu_sh;     /* [P,M,3] nullable */
+  float coef_xyz, coef_dc, coef_sh;
+  double* sums;
+} DgrAdmmPenalty;
+
 typedef struct DgrParams {
   int32_t P;               /* number of Gaussians                                   */
   int32_t D;               /* active SH degree 0..3  (raster_settings.sh_degree)    */
@@ -54,6 +67,7 @@ typedef struct DgrParams {
       instantiated 1-D on a 16x16 block (forward.cu:495-500), which only reduces the tile's first
       warp (pixel rows 0-1), so PerGaussianRenderCUDA (backward.cu:505-507) drops every 32-splat
       bucket starting at or after max(n_contrib of rows 0-1).  See DESIGN.md "Reference defect". */
+  const DgrAdmmPenalty* admm;    /* backward only, host pointer, nullable (see DgrAdmmPenalty) */
 } DgrParams;
 
 /* Sizes / counters reported by dgr_forward (host side). */

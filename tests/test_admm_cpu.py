@@ -43,6 +43,8 @@ class OracleOps:
 
     def penalty(self, x, u, z, grads, n, coef, sums):
         for g in range(6):
+            if x[g] is None:
+                continue
             r = (x[g] + u[g]) - z[g] if u is not None else x[g] - z[g]
             sums[g] += (r.double() ** 2).sum()
             if grads is not None:

@@ -34,9 +34,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from dogs_b200 import _lib
-    # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 1 int (+ padding to 8)
-    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8
+    # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 1 int (+ padding to 8), 1 pointer
+    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8
     assert _lib.DgrParams.bg.offset == 48 and _lib.DgrParams.ref_bucket_cull_quirk.offset == 80
+    assert _lib.DgrParams.admm.offset == 88
+    assert C.sizeof(_lib.DgrAdmmPenalty) == 3 * 8 + 3 * 4 + 4 + 8
     assert C.sizeof(_lib.DgrLayout) == 11 * 8
     assert C.sizeof(_lib.AdmmTensors) == 48
 

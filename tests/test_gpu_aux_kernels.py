@@ -184,3 +184,48 @@ def test_admm_consensus_kernels_vs_oracle():
     assert np.allclose(pens, pens_ref, rtol=1e-5, atol=1e-12)
     for g in range(6):
         assert np.abs(grads[g].cpu().numpy() - grads_ref[g]).max() <= 1e-6 * max(1.0, np.abs(grads_ref[g]).max())
+
+
+def test_fused_admm_penalty_in_rasterizer_backward_matches_standalone():
+    """DgrAdmmPenalty: the rasterizer backward adds the xyz / f_dc / f_rest penalty gradients itself;
+    the result must equal rasterizer gradient + standalone admm_penalty (all six groups)."""
+    from dogs_b200 import admm as A, scenes
+    import dogs_b200.diff_gaussian_rasterization as dgr
+    sc = scenes.make_scene("tiny", 11, DEV)
+    P = sc["means3D"].shape[0]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    w = torch.randn(3, sc["H"], sc["W"], generator=g).to(DEV)
+
+    def leaves():
+        d = {"means3D": sc["means3D"].clone(), "dc": sc["dc"].reshape(P, 3).clone(), "sh": sc["sh"].reshape(P, 45).clone(),
+             "scales": sc["scales"].clone(), "rotations": sc["rotations"].clone(), "opacities": sc["opacities"].clone()}
+        for v in d.values():
+            v.requires_grad_(True)
+        return d
+
+    def run(fused):
+        lv = leaves()
+        plan = A.ConsensusPlan(torch.arange(P, device=DEV), torch.full((P,), 2, dtype=torch.int32, device=DEV))
+        x = [lv[k] for k in ("means3D", "dc", "sh", "scales", "rotations", "opacities")]
+        blk = A.AdmmBlock(x, plan, alphas=(3e3, 2e3, 5e3, 1e3, 7e3, 9e2))
+        gg = torch.Generator(device="cpu").manual_seed(5)
+        for t in blk.zmu:                                   # pretend a consensus round happened
+            t.add_(0.05 * torch.randn(t.shape, generator=gg).to(DEV))
+        blk.fuse_into_rasterizer(fused)
+        try:
+            views = dict(lv)
+            views["dc"] = lv["dc"].view(P, 1, 3)
+            views["sh"] = lv["sh"].view(P, 15, 3)
+            img, _, _, _ = scenes.render(dgr, sc, views)
+            (img * w).sum().backward()
+            pens = blk.add_penalty_grads_()
+        finally:
+            blk.fuse_into_rasterizer(False)
+        torch.cuda.synchronize()
+        return {k: v.grad.clone() for k, v in lv.items()}, pens.clone()
+
+    g0, p0 = run(False)
+    g1, p1 = run(True)
+    assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-15)
+    for k in g0:
+        assert U.rel_to_max(g1[k], g0[k]) <= 2e-6, k
