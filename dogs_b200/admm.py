@@ -148,6 +148,7 @@ class AdmmBlock:
         self.pen_sums = torch.zeros(6, dtype=torch.float64, device=dev)
         self.fused_sums = torch.zeros(3, dtype=torch.float64, device=dev)
         self.fused = False
+        self._pen_scale, self._pen_scale_key = None, None
         self.last_primal: Optional[List[float]] = None
         self.last_dual: Optional[List[float]] = None
 
@@ -216,8 +217,14 @@ class AdmmBlock:
         if self.fused:
             self.pen_sums[:3] += self.fused_sums
             self.fused_sums.zero_()
-        scale = torch.tensor([0.5 * c for c in coef], dtype=torch.float64, device=self.pen_sums.device)
-        return self.pen_sums * scale
+        # penalties_g = 0.5 * rho_g/numel_g * sum r^2; the scale vector lives on the device and is only
+        # rebuilt when rho changes (no host->device copy, no sync, in the per-iteration path)
+        key = tuple(coef)
+        if self._pen_scale_key != key:
+            self._pen_scale = torch.tensor([0.5 * c for c in coef], dtype=torch.float64,
+                                           device=self.pen_sums.device)
+            self._pen_scale_key = key
+        return self.pen_sums * self._pen_scale
 
     def state_dict(self):
         """What a checkpoint must persist for ADMM (slave:209-263 stores u_*, rho_*; the reference does
