@@ -14,8 +14,8 @@
 namespace dogs {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 
