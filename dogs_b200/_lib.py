@@ -30,6 +30,7 @@ class DgrParams(C.Structure):
         ("campos", C.c_void_p),
         ("ref_bucket_cull_quirk", C.c_int32),
         ("admm", C.POINTER(DgrAdmmPenalty)),
+        ("gaussians_count", C.c_void_p), ("important_score", C.c_void_p),
     ]
 
 

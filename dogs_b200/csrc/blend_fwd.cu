@@ -18,15 +18,25 @@
 
 namespace dogs {
 
+// COUNT = true additionally counts, per Gaussian, the pixels it was blended into (LightGaussian
+// importance statistics: renderCUDA_count of the reference's older rasterizer,
+// submodules/old_diff-gaussian-rasterization/cuda_rasterizer/forward.cu:400-513, whose
+// `gaussian_count[id]++` is a non-atomic race; here the lanes of a warp are tallied with a ballot,
+// tiles add up in shared memory and one integer atomic per (tile, Gaussian) reaches global memory).
+template <bool COUNT>
 __global__ void __launch_bounds__(TILE_PIX)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
                  int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                  float* __restrict__ out_color, float* __restrict__ invdepth,
-                 float* __restrict__ pix_color, float* __restrict__ pix_invdepth) {
+                 float* __restrict__ pix_color, float* __restrict__ pix_invdepth,
+                 int* __restrict__ gaussian_count) {
   __shared__ float4 sA[2][TILE_PIX];
   __shared__ float4 sB[2][TILE_PIX];
   __shared__ float4 sC[2][TILE_PIX];
+  __shared__ uint32_t sId[COUNT ? 2 : 1][COUNT ? TILE_PIX : 1];
+  __shared__ int sCnt[COUNT ? TILE_PIX : 1];
+  if (COUNT) sCnt[threadIdx.x] = 0;
   const uint32_t tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
@@ -51,7 +61,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   auto fetch = [&](int round, int buf) {
     uint32_t progress = range.x + round * TILE_PIX + tid;
     if (progress < range.y) {
-      const SplatRecord* r = rec + point_list[progress];
+      const uint32_t id = point_list[progress];
+      if (COUNT) sId[buf][tid] = id;
+      const SplatRecord* r = rec + id;
       cp_async16(&sA[buf][tid], &r->a);
       cp_async16(&sB[buf][tid], &r->b);
       cp_async16(&sC[buf][tid], &r->c);
@@ -91,28 +103,42 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         if (__all_sync(0xffffffffu, done)) { m = 0; break; }
         const int j = r * 32 + __ffs(m) - 1;
         m &= m - 1;
-        if (done) continue;
-        const float4 con_o = sA[buf][j];
-        const float4 b = sB[buf][j];
-        float2 xy = {b.x, b.y};
-        float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-        float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-        if (power > 0.0f) continue;
-        float alpha = min(0.99f, con_o.w * exp(power));
-        if (alpha < 1.0f / 255.0f) continue;
-        float test_T = T * (1 - alpha);
-        if (test_T < 0.0001f) {
-          done = true;
-          continue;
+        bool blended = false;
+        if (!done) {
+          const float4 con_o = sA[buf][j];
+          const float4 b = sB[buf][j];
+          float2 xy = {b.x, b.y};
+          float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+          float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+          if (!(power > 0.0f)) {
+            float alpha = min(0.99f, con_o.w * exp(power));
+            if (!(alpha < 1.0f / 255.0f)) {
+              float test_T = T * (1 - alpha);
+              if (test_T < 0.0001f) {
+                done = true;
+              } else {
+                const float4 c = sC[buf][j];
+                C[0] += b.w * alpha * T;
+                C[1] += c.x * alpha * T;
+                C[2] += c.y * alpha * T;
+                expected_invdepth += b.z * alpha * T;
+                T = test_T;
+                last_contributor = base + j + 1;   // forward.cu:444,479: position in the tile's list
+                blended = true;
+              }
+            }
+          }
         }
-        const float4 c = sC[buf][j];
-        C[0] += b.w * alpha * T;
-        C[1] += c.x * alpha * T;
-        C[2] += c.y * alpha * T;
-        expected_invdepth += b.z * alpha * T;
-        T = test_T;
-        last_contributor = base + j + 1;   // forward.cu:444,479: position in the tile's list
+        if (COUNT) {
+          const uint32_t n = __popc(__ballot_sync(0xffffffffu, blended));
+          if (lane == 0 && n) atomicAdd(&sCnt[j], (int)n);
+        }
       }
+    }
+    if (COUNT) {   // flush this batch's tallies: thread t owns entry t
+      __syncthreads();
+      if ((int)tid < nbatch && sCnt[tid]) atomicAdd(&gaussian_count[sId[buf][tid]], sCnt[tid]);
+      sCnt[tid] = 0;
     }
   }
   cp_async_wait<0>();
@@ -132,12 +158,31 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
 }
 
+// important_score[id] = sum over the blended pixels of conic_opacity.w (old forward.cu:486), i.e.
+// count * opacity; written for every Gaussian (0 where count == 0).
+__global__ void importance_kernel(int P, const int* __restrict__ count, const SplatRecord* __restrict__ rec,
+                                  float* __restrict__ score) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int c = count[i];
+  score[i] = c ? (float)c * rec[i].a.w : 0.f;
+}
+
 int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
                      float* out_color, float* out_invdepth, cudaStream_t s) {
   dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
-  blend_fwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
-                                             im.final_T, im.n_contrib, out_color, out_invdepth,
-                                             im.pix_color, im.pix_invdepth);
+  if (prm.gaussians_count) {
+    cudaMemsetAsync(prm.gaussians_count, 0, (size_t)prm.P * sizeof(int32_t), s);
+    blend_fwd_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+                                                     im.final_T, im.n_contrib, out_color, out_invdepth,
+                                                     im.pix_color, im.pix_invdepth, prm.gaussians_count);
+    if (prm.important_score)
+      importance_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, prm.gaussians_count, g.rec, prm.important_score);
+    return check_launch("blend_fwd(count)", prm.debug != 0, s, prm.important_score ? 2 : 1);
+  }
+  blend_fwd_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+                                                    im.final_T, im.n_contrib, out_color, out_invdepth,
+                                                    im.pix_color, im.pix_invdepth, nullptr);
   return check_launch("blend_fwd", prm.debug != 0, s);
 }
 

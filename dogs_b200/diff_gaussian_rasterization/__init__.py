@@ -33,8 +33,13 @@ class GaussianRasterizationSettings(NamedTuple):  # reference __init__.py:203-21
     campos: torch.Tensor
     prefiltered: bool
     debug: bool
-    antialiasing: bool
-    depth_threshold: float
+    # The reference declares the next two without defaults; its own count_render()
+    # (conerf/render/gaussian_render.py:198-213) omits `antialiasing` and passes `f_count`, which the
+    # shipped rasterizer rejects with a TypeError.  Defaults + the extra f_count field make both call
+    # styles work.
+    antialiasing: bool = False
+    depth_threshold: float = 0.0
+    f_count: bool = False       # LightGaussian importance statistics (old rasterizer's count mode)
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -87,6 +92,42 @@ def rasterize_gaussians(means3D, means2D, dc, sh, colors_precomp, opacities, sca
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, dc, sh, colors_precomp, opacities, scales,
                                      rotations, cov3Ds_precomp, raster_settings)
+
+
+@torch.no_grad()
+def rasterize_gaussians_count(means3D, dc, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                              raster_settings):
+    """Count mode of the reference's older rasterizer (old_diff_gaussian_rasterization/__init__.py:
+    f_count=True): returns (gaussians_count[P] int32, important_score[P] float32, color[3,H,W], radii[P]).
+    Not differentiable (prune.py calls it under no_grad)."""
+    rs = raster_settings
+    means3D, dc, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = map(
+        _c, (means3D, dc, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp))
+    device = means3D.device
+    P = means3D.size(0)
+    if colors_precomp.numel() == 0 and dc.numel() == 0 and sh.numel() != 0:
+        dc, sh = sh[:, :1].contiguous(), sh[:, 1:].contiguous()
+    M = sh.size(1) if sh.numel() != 0 else 0
+    H, W = int(rs.image_height), int(rs.image_width)
+    color = torch.zeros((3, H, W), dtype=torch.float32, device=device)
+    invdepth = torch.empty((1, H, W), dtype=torch.float32, device=device)
+    radii = torch.zeros((P,), dtype=torch.int32, device=device)
+    count = torch.zeros((P,), dtype=torch.int32, device=device)
+    score = torch.zeros((P,), dtype=torch.float32, device=device)
+    if P != 0:
+        prm, keep = _params(rs, P, M, device)
+        prm.gaussians_count = count.data_ptr()
+        prm.important_score = score.data_ptr()
+        allocs = [L.Allocator(device) for _ in range(4)]
+        info = L.DgrForwardInfo()
+        with torch.cuda.device(device):
+            L.check(L.lib().dgr_forward(
+                C.byref(prm), L.ptr(means3D), L.ptr(dc), L.ptr(sh), L.ptr(colors_precomp), L.ptr(opacities),
+                L.ptr(scales), L.ptr(rotations), L.ptr(cov3Ds_precomp), color.data_ptr(), invdepth.data_ptr(),
+                radii.data_ptr(), allocs[0].cb, None, allocs[1].cb, None, allocs[2].cb, None, allocs[3].cb, None,
+                C.byref(info), L.stream_ptr(device)))
+        del keep
+    return count, score, color, radii
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -240,6 +281,9 @@ class GaussianRasterizer(nn.Module):  # reference __init__.py:220-300
             rotations = torch.Tensor([])
         if cov3D_precomp is None:
             cov3D_precomp = torch.Tensor([])
+        if getattr(raster_settings, "f_count", False):
+            return rasterize_gaussians_count(means3D, dc, shs, colors_precomp, opacities, scales, rotations,
+                                             cov3D_precomp, raster_settings)
         return rasterize_gaussians(means3D, means2D, dc, shs, colors_precomp, opacities, scales,
                                    rotations, cov3D_precomp, raster_settings)
 

@@ -68,6 +68,12 @@ typedef struct DgrParams {
       warp (pixel rows 0-1), so PerGaussianRenderCUDA (backward.cu:505-507) drops every 32-splat
       bucket starting at or after max(n_contrib of rows 0-1).  See DESIGN.md "Reference defect". */
   const DgrAdmmPenalty* admm;    /* backward only, host pointer, nullable (see DgrAdmmPenalty) */
+  /* forward only, nullable device pointers: LightGaussian importance statistics (count mode of the
+   * reference's older rasterizer, old_diff-gaussian-rasterization/cuda_rasterizer/forward.cu:400-513,
+   * consumed by conerf/model/gaussian_fields/prune.py:13-65): gaussians_count[P] = number of pixels
+   * each Gaussian was blended into, important_score[P] = that count times its (anti-aliased) opacity. */
+  int32_t* gaussians_count;
+  float* important_score;
 } DgrParams;
 
 /* Sizes / counters reported by dgr_forward (host side). */

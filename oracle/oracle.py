@@ -83,16 +83,21 @@ def binning(s, pre):
     return dict(keys=keys, point_list=vals, ranges=ranges, counts=counts, keys_unsorted=unsorted_keys)
 
 
-def render_fwd(s, pre, bins, bg=None, tile_sel=None):
+def render_fwd(s, pre, bins, bg=None, tile_sel=None, count=False):
     """forward.cu:349-501."""
     W, H = int(s["W"]), int(s["H"])
     bg = np.zeros(3, np.float32) if bg is None else _f32(bg)
     o = dict(color=np.zeros((3, H, W), np.float32), invdepth=np.zeros((1, H, W), np.float32),
              final_T=np.zeros(H * W, np.float32), n_contrib=np.zeros(H * W, np.uint32))
+    cnt = np.zeros(pre["radii"].shape[0], np.int32) if count else None
     lib().orc_render_fwd(C.c_int(W), C.c_int(H), _p(bins["ranges"]), _p(bins["point_list"]),
                          _p(pre["means2D"]), _p(pre["rgb"]), _p(pre["conic_opacity"]),
                          _p(pre["depths"]), _p(bg), _p(o["color"]), _p(o["invdepth"]),
-                         _p(o["final_T"]), _p(o["n_contrib"]), _p(tile_sel))
+                         _p(o["final_T"]), _p(o["n_contrib"]), _p(tile_sel), _p(cnt))
+    if count:
+        # old_diff-gaussian-rasterization forward.cu:485-486: count++ and score += conic_opacity.w per blended pixel
+        o["gaussians_count"] = cnt
+        o["important_score"] = (cnt.astype(np.float32) * pre["conic_opacity"][:, 3]).astype(np.float32)
     return o
 
 

@@ -229,3 +229,37 @@ def test_fused_admm_penalty_in_rasterizer_backward_matches_standalone():
     assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-15)
     for k in g0:
         assert U.rel_to_max(g1[k], g0[k]) <= 2e-6, k
+
+
+def test_importance_count_render_vs_oracle():
+    """f_count mode (LightGaussian statistics): counts are exact integers, so they must equal the
+    oracle's wherever its n_contrib agrees (libm-vs-libdevice expf flips aside), and the image is the
+    ordinary render."""
+    from dogs_b200 import scenes
+    import dogs_b200.diff_gaussian_rasterization as dgr
+    from oracle import oracle as O
+    sc = scenes.make_scene("tiny", 12, DEV)
+    rs = scenes.raster_settings(dgr, sc)._replace(f_count=True)
+    rast = dgr.GaussianRasterizer(rs)
+    cnt, score, img, radii = rast(means3D=sc["means3D"], means2D=torch.zeros_like(sc["means3D"]), opacities=sc["opacities"],
+                                  dc=sc["dc"], shs=sc["sh"], scales=sc["scales"], rotations=sc["rotations"])
+    ref_img = scenes.render(dgr, sc)[0]
+    assert torch.equal(img, ref_img)
+    s = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+    pre = O.preprocess(s)
+    bins = O.binning(s, pre)
+    o = O.render_fwd(s, pre, bins, count=True)
+    c = cnt.cpu().numpy()
+    assert int(c.sum()) > 0 and c.dtype == np.int32
+    assert int(np.abs(c.astype(np.int64) - o["gaussians_count"]).sum()) <= 8      # expf threshold flips only
+    same = c == o["gaussians_count"]
+    assert np.allclose(score.cpu().numpy()[same], o["important_score"][same], rtol=1e-6)
+    assert int((c[radii.cpu().numpy() == 0] != 0).sum()) == 0
+    # the call style of the reference's count_render(): keywords, no `antialiasing`, f_count=True
+    rs2 = dgr.GaussianRasterizationSettings(image_height=sc["H"], image_width=sc["W"], tanfovx=sc["tanfovx"],
+                                            tanfovy=sc["tanfovy"], bg=torch.zeros(3, device=DEV), scale_modifier=1.0,
+                                            depth_threshold=0.0, viewmatrix=sc["viewmatrix"], projmatrix=sc["projmatrix"],
+                                            sh_degree=3, campos=sc["campos"], prefiltered=False, debug=False, f_count=True)
+    out = dgr.GaussianRasterizer(rs2)(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"],
+                                      shs=torch.cat([sc["dc"], sc["sh"]], 1), scales=sc["scales"], rotations=sc["rotations"])
+    assert len(out) == 4 and torch.equal(out[0], cnt)
