@@ -67,6 +67,8 @@ SIGNATURES = {
     "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
     "dgr_sparse_adam": [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
                         C.c_uint32, C.c_uint32, _P],
+    "dgr_compact_plan": [C.c_int64, _P, _P, ALLOC_FN, _P, C.POINTER(C.c_int64), _P],
+    "dgr_compact_rows": [C.c_int64, C.c_int32, _P, _P, _P, _P, _P],
     "fssim_forward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 6 + [_P],
     "fssim_backward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 7 + [_P],
     "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],

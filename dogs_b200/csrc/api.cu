@@ -33,7 +33,7 @@ int check_launch(const char* what, bool debug, cudaStream_t s, int kernels) {
 size_t GeomState::bytes(size_t P) {
   Carver c(nullptr);
   c.take<SplatRecord>(P); c.take<uint8_t>(P); c.take<uint32_t>(P); c.take<uint32_t>(P);
-  c.take<uint32_t>(P); c.take<uint32_t>(P); c.take<unsigned long long>(P);
+  c.take<uint32_t>(P); c.take<uint32_t>(P); c.take<uint4>(P); c.take<uint4>(P); c.take<uint32_t>(P);
   return c.off;
 }
 GeomState GeomState::carve(char* p, size_t P) {
@@ -45,7 +45,9 @@ GeomState GeomState::carve(char* p, size_t P) {
   g.depth_key = c.take<uint32_t>(P);
   g.sorted_idx = c.take<uint32_t>(P);
   g.offsets = c.take<uint32_t>(P);
-  g.tile_mask = c.take<unsigned long long>(P);
+  g.emit_rec = c.take<uint4>(P);
+  g.sorted_emit = c.take<uint4>(P);
+  g.sorted_cnt = c.take<uint32_t>(P);
   return g;
 }
 size_t BinState::bytes(size_t R) {
@@ -187,7 +189,10 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     // 4 passes of 8 bits => the result is back in (depth_key, sorted_idx)
     if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b)) return 1;
     if (in_b) cudaMemcpyAsync(g.sorted_idx, vals_b, P * 4, cudaMemcpyDeviceToDevice, s);
-    if (exclusive_scan_u32(g.tiles, g.sorted_idx, g.offsets, total, P, scan_scratch, dbg, s)) return 1;
+    // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
+    // the scan and the emit kernel then stream sequentially
+    if (launch_gather_emit(p, g, s)) return 1;
+    if (exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, total, P, scan_scratch, dbg, s)) return 1;
     // the one host synchronisation of the forward pass (the reference has two:
     // rasterizer_impl.cu:423,469): the instance count sizes the binning buffers.
     cudaError_t e = cudaMemcpyAsync(&R, total, 4, cudaMemcpyDeviceToHost, s);

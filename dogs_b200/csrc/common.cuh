@@ -152,7 +152,11 @@ struct GeomState {
   SplatRecord* rec; uint8_t* clamped; uint32_t* tiles; uint32_t* depth_key;
   uint32_t* sorted_idx;    // Gaussian ids in depth order
   uint32_t* offsets;       // exclusive scan of tiles in depth order
-  unsigned long long* tile_mask;  // reachable tiles of the rect (bit = row-major index), rect area <= 64
+  // per Gaussian: {rect word, instance count, reachable-tile mask (bit = row-major index in the rect)};
+  // rect word = min.x | min.y << 11 | width << 22, width 0 = rect larger than 64 tiles (mask unused)
+  uint4* emit_rec;
+  uint4* sorted_emit;      // the same in depth order, .y replaced by the Gaussian id
+  uint32_t* sorted_cnt;    // instance counts in depth order (scan input)
   static size_t bytes(size_t P);
   static GeomState carve(char* p, size_t P);
 };
@@ -187,6 +191,7 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
                           const float* sh, const float* colors_precomp, const float* opacities,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           int32_t* radii, GeomState& g, cudaStream_t s);
+int launch_gather_emit(const DgrParams& prm, const GeomState& g, cudaStream_t s);
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
                 uint32_t* vals, cudaStream_t s);
 int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,

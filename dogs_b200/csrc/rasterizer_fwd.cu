@@ -102,7 +102,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
                       int* __restrict__ radii, SplatRecord* __restrict__ rec,
                       uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
-                      uint32_t* __restrict__ depth_key, unsigned long long* __restrict__ tile_mask,
+                      uint32_t* __restrict__ depth_key, uint4* __restrict__ emit_rec,
                       uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing) {
   extern __shared__ float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
@@ -128,6 +128,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   int radius_out = 0;
   uint32_t ntiles = 0, dkey = 0xffffffffu;
   unsigned long long mask = 0ull;
+  uint32_t rect_word = 0;
   do {
     float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
     // auxiliary.h:150-175 in_frustum
@@ -200,7 +201,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     rec[idx] = r;
 
     const int rw = rect_max.x - rect_min.x;
-    const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64;   // mask of reachable tiles fits 64 bits
+    const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64 && rect_min.x < 2048u && rect_min.y < 2048u;
+    rect_word = small ? (rect_min.x | (rect_min.y << 11) | ((uint32_t)rw << 22)) : 0u;   // mask fits 64 bits
     for (int y = rect_min.y; y < (int)rect_max.y; y++)
       for (int x = rect_min.x; x < (int)rect_max.x; x++)
         if (tile_reachable(co, point_image, x, y, thr)) {
@@ -211,44 +213,56 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   } while (0);
   radii[idx] = radius_out;
   tiles[idx] = ntiles;
-  tile_mask[idx] = mask;
+  emit_rec[idx] = make_uint4(rect_word, ntiles, (uint32_t)mask, (uint32_t)(mask >> 32));
   depth_key[idx] = ntiles ? dkey : 0xffffffffu;
 }
 
-// One thread per depth-sorted position: re-walk the rect and write (tile id, Gaussian id) for
-// every reachable tile (the emitting half of duplicateWithKeys).  Instances are therefore
-// already in (depth, Gaussian id) order; the stable sort by tile id that follows reproduces the
-// order of the reference's 64-bit (tile|depth) sort without ever materialising 64-bit keys.
+// emit_rec -> depth order (one 16-byte gather per Gaussian); .y becomes the Gaussian id.
 __global__ void __launch_bounds__(256)
-emit_instances_kernel(int P, const uint32_t* __restrict__ sorted_idx,
-                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ tiles,
-                      const unsigned long long* __restrict__ tile_mask,
-                      const SplatRecord* __restrict__ rec, const int* __restrict__ radii,
-                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, uint32_t gx,
-                      uint32_t gy) {
+gather_emit_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* __restrict__ emit_rec,
+                   uint4* __restrict__ sorted_emit, uint32_t* __restrict__ sorted_cnt) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  const uint32_t id = sorted_idx[j];
+  const uint4 e = emit_rec[id];
+  sorted_cnt[j] = e.y;
+  sorted_emit[j] = make_uint4(e.x, id, e.z, e.w);
+}
+
+// One thread per depth-sorted position: write (tile id, Gaussian id) for every reachable tile (the
+// emitting half of duplicateWithKeys, rasterizer_impl.cu:151-177).  Instances are therefore already
+// in (depth, Gaussian id) order; the stable sort by tile id that follows reproduces the order of
+// the reference's 64-bit (tile|depth) sort without ever materialising 64-bit keys.  The common case
+// (rect of <= 64 tiles) just walks the bit mask recorded by preprocess; larger rects re-run the test.
+__global__ void __launch_bounds__(256)
+emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32_t* __restrict__ sorted_cnt,
+                      const uint32_t* __restrict__ offsets, const SplatRecord* __restrict__ rec,
+                      const int* __restrict__ radii, uint32_t* __restrict__ tile_keys,
+                      uint32_t* __restrict__ vals, uint32_t gx, uint32_t gy) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  const uint32_t idx = sorted_idx[i];
-  if (tiles[idx] == 0) return;
+  if (sorted_cnt[i] == 0) return;
+  const uint4 e = sorted_emit[i];
+  const uint32_t idx = e.y;
   uint32_t off = offsets[i];
-  const float4 b = rec[idx].b;
-  const float2 xy = {b.x, b.y};
-  uint2 rect_min, rect_max;
-  get_rect(xy, radii[idx], rect_min, rect_max, gx, gy);
-  const int rw = rect_max.x - rect_min.x;
-  if (rw * (int)(rect_max.y - rect_min.y) <= 64) {
-    // common case: preprocess already recorded which tiles of the rect are reachable
-    unsigned long long m = tile_mask[idx];
+  const uint32_t rw = e.x >> 22;
+  if (rw) {
+    const uint32_t x0 = e.x & 2047u, y0 = (e.x >> 11) & 2047u;
+    unsigned long long m = ((unsigned long long)e.w << 32) | e.z;
     while (m) {
       const int bit = __ffsll((long long)m) - 1;
       m &= m - 1;
-      const int ty = bit / rw, tx = bit - ty * rw;
-      tile_keys[off] = (rect_min.y + ty) * gx + rect_min.x + tx;
+      const uint32_t ty = bit / rw, tx = bit - ty * rw;
+      tile_keys[off] = (y0 + ty) * gx + x0 + tx;
       vals[off] = idx;
       off++;
     }
     return;
   }
+  const float4 b = rec[idx].b;
+  const float2 xy = {b.x, b.y};
+  uint2 rect_min, rect_max;
+  get_rect(xy, radii[idx], rect_min, rect_max, gx, gy);
   const float4 co = rec[idx].a;
   const float thr = logf(co.w / (1.0f / 255.0f));
   for (int y = rect_min.y; y < (int)rect_max.y; y++)
@@ -362,16 +376,21 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
       prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
       cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
       prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
-      g.tile_mask, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
+      g.emit_rec, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
   return check_launch("preprocess_fwd", prm.debug != 0, s);
+}
+
+int launch_gather_emit(const DgrParams& prm, const GeomState& g, cudaStream_t s) {
+  gather_emit_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_idx, g.emit_rec, g.sorted_emit,
+                                                         g.sorted_cnt);
+  return check_launch("gather_emit", prm.debug != 0, s);
 }
 
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
                 uint32_t* vals, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
-  emit_instances_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_idx, g.offsets, g.tiles,
-                                                            g.tile_mask, g.rec, radii, tile_keys, vals,
-                                                            gx, gy);
+  emit_instances_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_emit, g.sorted_cnt, g.offsets,
+                                                            g.rec, radii, tile_keys, vals, gx, gy);
   return check_launch("emit_instances", prm.debug != 0, s);
 }
 

@@ -161,6 +161,15 @@ int dgr_sparse_adam(float* param, const float* grad, float* exp_avg, float* exp_
                     const uint8_t* visible, float lr, float b1, float b2, float eps,
                     uint32_t N, uint32_t M, void* stream);
 
+/* ---- stream compaction of the Gaussian SoA (prune / densify) ----------------
+ * Replaces boolean-mask indexing of the 6 parameter tensors and their Adam state
+ * (conerf/model/gaussian_fields/gaussian_splat_model.py:34-108,362-531). */
+int dgr_compact_plan(int64_t P, const uint8_t* keep, uint32_t* offsets,
+                     dogs_alloc_fn scratch_alloc, void* scratch_user, int64_t* count_out /* host */,
+                     void* stream);
+int dgr_compact_rows(int64_t P, int32_t row_words, const void* src, void* dst,
+                     const uint8_t* keep, const uint32_t* offsets, void* stream);
+
 /* ---- fused-SSIM (submodules/fused-ssim/ssim.cu:368-444) ------------------------- */
 int fssim_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
                   const float* img1, const float* img2, float* ssim_map,

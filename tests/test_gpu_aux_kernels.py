@@ -263,3 +263,18 @@ def test_importance_count_render_vs_oracle():
     out = dgr.GaussianRasterizer(rs2)(means3D=sc["means3D"], means2D=None, opacities=sc["opacities"],
                                       shs=torch.cat([sc["dc"], sc["sh"]], 1), scales=sc["scales"], rotations=sc["rotations"])
     assert len(out) == 4 and torch.equal(out[0], cnt)
+
+
+def test_compaction_equals_boolean_indexing():
+    """dogs_b200.compaction.compact == [t[mask] for t in tensors] (prune bookkeeping)."""
+    from dogs_b200.compaction import compact
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for P in (1, 7, 100_003):
+        ts = [torch.randn(P, 3, generator=g).to(DEV), torch.randn(P, 15, 3, generator=g).to(DEV),
+              torch.randn(P, 1, generator=g).to(DEV), torch.randn(P, 4, generator=g).to(DEV),
+              torch.randint(0, 1000, (P,), generator=g, dtype=torch.int32).to(DEV)]
+        for frac in (0.0, 0.37, 1.0):
+            keep = (torch.rand(P, generator=g) < frac).to(DEV)
+            out = compact(ts, keep)
+            for a, t in zip(out, ts):
+                assert a.shape == t[keep].shape and torch.equal(a, t[keep])
