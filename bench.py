@@ -446,11 +446,25 @@ def blend_bwd_roofline(sc, dev, reps=10):
     peak, how = peaks()
     alg_bytes = 44.0 * R + 44.0 * N + 40.0 * R
     achieved = alg_bytes / (best[0] * 1e-3) / 1e9
+    traffic, issue = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and sc["name"] == "C3":
+        with open(tpath) as f:
+            t = json.load(f).get("blend_bwd_kernel", {})
+        traffic = t.get("dram_bytes")
+        if t.get("warp_instructions"):
+            # issue-slot roofline: 148 SMs x 4 schedulers x 1 warp instruction / clock at the max SM clock
+            issue_peak = 148 * 4 * 1.965e9
+            issue = {"warp_instructions": t["warp_instructions"],
+                     "achieved_ginst_s": t["warp_instructions"] / (best[0] * 1e-3) / 1e9,
+                     "peak_ginst_s": issue_peak / 1e9,
+                     "frac": t["warp_instructions"] / (best[0] * 1e-3) / issue_peak,
+                     "source": "ncu smsp__inst_executed.sum of the committed capture / live kernel time"}
     roof = {"kernel": "blend_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": how, "kernel_ms": best[0],
-            "algorithmic_bytes": alg_bytes,
-            "note": "the kernel is FP32-issue bound (no dense contraction): "
-                    f"{sum_nc} contributing (pixel,splat) pairs; preprocess_bwd_kernel {best[1]:.3f} ms"}
+            "frac": achieved / peak, "traffic": traffic, "peak_source": how, "kernel_ms": best[0],
+            "algorithmic_bytes": alg_bytes, "issue": issue,
+            "note": "instruction-issue bound, not HBM bound (no stage is a dense contraction): "
+                    f"{sum_nc} visited (pixel,splat) pairs; preprocess_bwd_kernel {best[1]:.3f} ms"}
     return roof, stats
 
 
