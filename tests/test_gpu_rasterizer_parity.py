@@ -311,8 +311,21 @@ def test_full_size_properties(cfg):
         rb = U.parse_ref_binning(r["binning"], r["num_rendered"])
         valid = ((rb["keys"] >> 32) & 0xFFFFFFFF) != 0xFFFFFFFF
         assert torch.equal(rb["keys"][valid], keys)
+        # gradients at full size against the reference backward with the intended max_contrib
+        T = ((W + 15) // 16) * ((H + 15) // 16)
+        ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
+        dLc, dLd = _out_grads(sc)
+        gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+        gr = {k: gr[k].clone() for k in GRAD_KEYS}
         del r, ri, rb
-    del o, o2
+        del o, o2
+        torch.cuda.empty_cache()
+        go = U.ours_backward(sc, dLc, dLd)
+        for k in GRAD_KEYS:
+            assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, (k, U.rel_to_max(go[k], gr[k].reshape(go[k].shape)))
+        del go, gr
+    else:
+        del o, o2
     torch.cuda.empty_cache()
     dLc, dLd = _out_grads(sc)
     g1 = U.ours_backward(sc, dLc, dLd)
