@@ -315,14 +315,23 @@ def test_full_size_properties(cfg):
         T = ((W + 15) // 16) * ((H + 15) // 16)
         ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
         dLc, dLd = _out_grads(sc)
-        gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
-        gr = {k: gr[k].clone() for k in GRAD_KEYS}
-        del r, ri, rb
+        # The reference accumulates with float atomics in scheduling order, so at 3 M Gaussians its own
+        # gradients move from run to run (measured with tools/gpu_grad_noise.py on C3: rotations
+        # 1.8e-4, scales 4.9e-5 of max|g|, everything else <= 1.3e-6).  The bar for a tensor is
+        # GRAD_TOL or twice the reference's own spread over three runs, whichever is larger.
+        runs = []
+        for _ in range(3):
+            gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+            runs.append({k: gr[k].clone() for k in GRAD_KEYS})
+        gr = runs[0]
+        spread = {k: max(U.rel_to_max(runs[1][k], gr[k]), U.rel_to_max(runs[2][k], gr[k])) for k in GRAD_KEYS}
+        del r, ri, rb, runs
         del o, o2
         torch.cuda.empty_cache()
         go = U.ours_backward(sc, dLc, dLd)
         for k in GRAD_KEYS:
-            assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, (k, U.rel_to_max(go[k], gr[k].reshape(go[k].shape)))
+            err = U.rel_to_max(go[k], gr[k].reshape(go[k].shape))
+            assert err <= max(GRAD_TOL, 2.0 * spread[k]), (k, err, spread[k])
         del go, gr
     else:
         del o, o2
