@@ -184,18 +184,23 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int nbatch = min(BB_BATCH, (int)todo_total - i * BB_BATCH);
     const uint32_t base = i * BB_BATCH;
 
-    // Sub-tile culling (blend_common.cuh): which entries of the batch can reach this warp's 8x16
-    // half tile at all; one entry per lane and round.
-    uint32_t hm[2];
+    // Sub-tile culling (blend_common.cuh): which entries of the batch can reach each of the four 8x4
+    // blocks of this warp's half tile; one entry per lane and round, 4 mask bits per entry.
+    uint32_t hm[2], bm[2];
 #pragma unroll
     for (int w = 0; w < 2; w++) {
       const int jj = 32 * w + lane;
-      bool h = false;
+      uint32_t m4 = 0;
       if (jj < nbatch) {
         const float4 bb = sB[buf][jj];
-        h = block_reachable(sA[buf][jj], bb.x, bb.y, rx0, ry0, rx0 + 7.f, ry0 + 15.f, sC[buf][jj].w);
+        const float4 aa = sA[buf][jj];
+        const float thr = sC[buf][jj].w;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          m4 |= (uint32_t)block_reachable(aa, bb.x, bb.y, rx0, ry0 + 4.f * k, rx0 + 7.f, ry0 + 4.f * k + 3.f, thr) << k;
       }
-      hm[w] = __ballot_sync(0xffffffffu, h);
+      bm[w] = m4;
+      hm[w] = __ballot_sync(0xffffffffu, m4 != 0);
     }
 
 #pragma unroll
@@ -206,35 +211,32 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       m &= m - 1;
       const int j = 32 * w + bit;
       const uint32_t e = base + j;
+      const uint32_t mk = __shfl_sync(0xffffffffu, bm[w], bit);   // warp-uniform block mask of entry j
       const float4 con_o = sA[buf][j];
       const float4 b = sB[buf][j];
-      // Test the four pixels branch-free (independent chains => ILP); power, expf and the alpha
-      // threshold are the forward's own expressions, so the contribution decisions and T are those of
-      // the forward pass bit for bit.  (A fast ex2.approx exp was measured: 10 % faster, but the 1e-6
-      // relative change of G decorrelates ill-conditioned conic gradients from the reference's by up
-      // to 5e-4 of the tensor max, outside the 1e-4 parity bar.)
-      float dx[4], dy[4], G[4], al[4];
-      bool c[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        dx[k] = b.x - pxf[k];
-        dy[k] = b.y - pyf[k];
-        const float power = -0.5f * (con_o.x * dx[k] * dx[k] + con_o.z * dy[k] * dy[k]) - con_o.y * dx[k] * dy[k];
-        G[k] = exp(power);
-        al[k] = min(0.99f, con_o.w * G[k]);
-        c[k] = (e < last[k]) && !(power > 0.0f) && !(al[k] < 1.0f / 255.0f);   // backward.cu:592-600
-      }
-      if (!__any_sync(0xffffffffu, c[0] | c[1] | c[2] | c[3])) continue;
       const float4 cc = sC[buf][j];
       const float invd = b.z;
+      const float dx = b.x - pxf[0];
       float v[10];
 #pragma unroll
       for (int q = 0; q < 10; q++) v[q] = 0.f;
+      bool any_c = false;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        if (!__any_sync(0xffffffffu, c[k])) continue;       // warp-uniform: this 8x4 block is not reached
-        const float alpha = c[k] ? al[k] : 0.f;              // masked lanes: weight 0, T and S unchanged
-        const float Gk = c[k] ? G[k] : 0.f;                  // (exp(power) may be inf where power > 0)
+        if (!(mk & (1u << k))) continue;                    // warp-uniform: the splat cannot reach this 8x4 block
+        // power, expf and the alpha threshold are the forward's own expressions, so the contribution
+        // decisions and T are those of the forward pass bit for bit.  (A fast ex2.approx exp was
+        // measured: 10 % faster, but the 1e-6 relative change of G decorrelates ill-conditioned conic
+        // gradients from the reference's by up to 5e-4 of the tensor max, outside the 1e-4 parity bar.)
+        const float dy = b.y - pyf[k];
+        const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
+        const float G = exp(power);
+        const float al = min(0.99f, con_o.w * G);
+        const bool c = (e < last[k]) && !(power > 0.0f) && !(al < 1.0f / 255.0f);   // backward.cu:592-600
+        if (!__any_sync(0xffffffffu, c)) continue;
+        any_c = true;
+        const float alpha = c ? al : 0.f;              // masked lanes: weight 0, T and S unchanged
+        const float Gk = c ? G : 0.f;                  // (exp(power) may be inf where power > 0)
         // c . dL/dC + invd * dL/dD
         const float cd = b.w * dC0[k] + cc.x * dC1[k] + cc.y * dC2[k] + invd * dD[k];
         const float Tk = T[k];
@@ -242,7 +244,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float om = 1.0f - alpha;
         const float inv = __fdividef(1.0f, om);   // MUFU.RCP (<= 1 ulp): gradients carry a 1e-4 bar
         S[k] += weight * cd;
-        const float dL_dalpha = c[k] ? (cd * Tk + inv * (S[k] - bgT[k])) : 0.f;
+        const float dL_dalpha = c ? (cd * Tk + inv * (S[k] - bgT[k])) : 0.f;
         T[k] = Tk * om;
         v[6] += weight * dC0[k];
         v[7] += weight * dC1[k];
@@ -254,14 +256,15 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         // (The conic is applied to the mean terms per pixel: dx*cx + dy*cy cancels strongly for
         // elongated splats, and summing the two moments separately loses that cancellation.)
         const float q = Gk * dL_dalpha;
-        const float qx = q * dx[k], qy = q * dy[k];
+        const float qx = q * dx, qy = q * dy;
         v[0] += q;
-        v[1] += q * (dx[k] * con_o.x + dy[k] * con_o.y);
-        v[2] += q * (dy[k] * con_o.z + dx[k] * con_o.y);
-        v[3] += qx * dx[k];
-        v[4] += qx * dy[k];
-        v[5] += qy * dy[k];
+        v[1] += q * (dx * con_o.x + dy * con_o.y);
+        v[2] += q * (dy * con_o.z + dx * con_o.y);
+        v[3] += qx * dx;
+        v[4] += qx * dy;
+        v[5] += qy * dy;
       }
+      if (!any_c) continue;
       const float tot = bb_warp_reduce10(v, lane);
       if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
     }

