@@ -28,7 +28,7 @@ class DgrParams(C.Structure):
         ("prefiltered", C.c_int32), ("antialiasing", C.c_int32), ("debug", C.c_int32),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
         ("campos", C.c_void_p),
-        ("ref_bucket_cull_quirk", C.c_int32),
+        ("ref_bucket_cull_quirk", C.c_int32), ("raw_inputs", C.c_int32),
         ("admm", C.POINTER(DgrAdmmPenalty)),
         ("gaussians_count", C.c_void_p), ("important_score", C.c_void_p),
     ]
@@ -64,6 +64,7 @@ SIGNATURES = {
                           + [_P] * 9 + [ALLOC_FN, _P, _P, _P],
     "dgr_visible_filter": [C.POINTER(DgrParams), _P, _P, _P, _P, _P, _P],
     "dgr_mark_visible": [C.c_int32, _P, _P, _P, _P, _P],
+    "dgr_apply_activations": [C.c_int32, _P, _P, _P, _P, _P, _P, _P],
     "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
     "dgr_sparse_adam": [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
                         C.c_uint32, C.c_uint32, _P],

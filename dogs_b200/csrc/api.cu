@@ -313,6 +313,18 @@ int dgr_backward_timed(const DgrParams* prm, int32_t num_rendered, const float* 
                        dL_drotations, dL_dcov3D, scratch_alloc, scratch_user, stream, stage_ms);
 }
 
+int dgr_apply_activations(int32_t P, const float* raw_opacities, const float* raw_scales,
+                          const float* raw_rotations, float* opacities, float* scales, float* rotations,
+                          void* stream) {
+  if (P < 0 || (raw_opacities && !opacities) || (raw_scales && !scales) || (raw_rotations && !rotations)) {
+    set_error("apply_activations: invalid arguments");
+    return 1;
+  }
+  if (P == 0) return 0;
+  return launch_activations(P, raw_opacities, raw_scales, raw_rotations, opacities, scales, rotations,
+                            (cudaStream_t)stream);
+}
+
 int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* scales,
                        const float* rotations, const float* cov3D_precomp, int32_t* radii,
                        void* stream) {

@@ -111,6 +111,24 @@ __device__ __forceinline__ void get_rect(const float2 p, int max_radius, uint2& 
           min(gy, (uint32_t)max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
 }
 
+// Activations the reference applies in torch before each render (gaussian_splat_model.py:148-153),
+// for DgrParams::raw_inputs.  Written to reproduce the torch CUDA kernels: sigmoid = 1/(1+exp(-x))
+// and exp with the full-precision expf and an IEEE divide; F.normalize(q, dim=1) = q / max(|q|, 1e-12)
+// with |q| = sqrt of the uncontracted squares summed in torch's reduction order.
+__device__ __forceinline__ float act_sigmoid(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ float3 act_exp3(float3 s) { return {expf(s.x), expf(s.y), expf(s.z)}; }
+__device__ __forceinline__ float quat_norm(float4 q) {
+  // torch 2.11's reduce kernel sums a 4-wide row as (x0^2 + x2^2) + (x1^2 + x3^2) (two shuffle steps);
+  // measured with tools/gpu_act_compare.py, where the other orders differ in ~4 % of the rows
+  const float ss = __fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.z, q.z)),
+                             __fadd_rn(__fmul_rn(q.y, q.y), __fmul_rn(q.w, q.w)));
+  return fmaxf(__fsqrt_rn(ss), 1e-12f);
+}
+__device__ __forceinline__ float4 act_normalize(float4 q) {
+  const float n = quat_norm(q);
+  return {__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n)};
+}
+
 // Per-tile reachability test of the key-duplication stage
 // (rasterizer_impl.cu:52-100 max_contrib_power_rect_gaussian_float<15,15> + :151-173).
 // Returns true iff the Gaussian can reach alpha >= 1/255 somewhere in tile (tx,ty).
@@ -198,6 +216,8 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_ke
                        cudaStream_t s);
 int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
                      float* out_color, float* out_invdepth, cudaStream_t s);
+int launch_activations(int P, const float* raw_op, const float* raw_sc, const float* raw_rot, float* op,
+                       float* sc, float* rot, cudaStream_t s);
 int launch_filter(const DgrParams& prm, const float* means3D, const float* scales,
                   const float* rotations, const float* cov3D_precomp, int32_t* radii, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,

@@ -168,7 +168,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       float* __restrict__ dL_ddc, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dcolors_precomp, float* __restrict__ dL_dopacity_out,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drots,
-                      float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm) {
+                      float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm, bool raw_inputs) {
   extern __shared__ float4 stage4[];
   float* stage = reinterpret_cast<float*>(stage4);
   const int first = blockIdx.x * PREB_THREADS;
@@ -217,7 +217,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
 
       const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
       float3 scale = {0.f, 0.f, 0.f};
-      float4 rot = {0.f, 0.f, 0.f, 0.f};
+      float4 rot = {0.f, 0.f, 0.f, 0.f}, raw_rot = {0.f, 0.f, 0.f, 0.f};
+      const float opac = raw_inputs ? act_sigmoid(opacities[idx]) : opacities[idx];
       float cov3D[6];
       M3 R, Mm;
       float3 s = {0.f, 0.f, 0.f};
@@ -227,6 +228,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       } else {
         scale = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
         rot = reinterpret_cast<const float4*>(rotations)[idx];
+        if (raw_inputs) { raw_rot = rot; scale = act_exp3(scale); rot = act_normalize(rot); }
         // forward.cu:119-153 / backward.cu:330-352
         const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
         R = m3(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
@@ -268,7 +270,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         const float det_cov_plus_h_cov = c_xx * c_yy - c_xy * c_xy;
         const float h_convolution_scaling = sqrt(max(0.000025f, det_cov / det_cov_plus_h_cov));
         const float dL_dopacity_v = dL_dopac;
-        const float d_h_convolution_scaling = dL_dopacity_v * opacities[idx];
+        const float d_h_convolution_scaling = dL_dopacity_v * opac;
         dL_dopac = dL_dopacity_v * h_convolution_scaling;
         d_inside_root = (det_cov / det_cov_plus_h_cov) <= 0.000025f
                             ? 0.f
@@ -376,6 +378,21 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         // reference returns dot(Rt[i], dL_dMt[i]) unscaled by mod (backward.cu:374-377); keep it.
       }
       g_opacity = dL_dopac;
+      if (raw_inputs) {
+        // chain rule through the activations, in the form of torch's own backward formulas
+        // (sigmoid_backward: g*(1-y)*y; exp: g*y; normalize = q / max(|q|, eps))
+        g_opacity = dL_dopac * (1.0f - opac) * opac;
+        if (cov3D_precomp == nullptr) {
+          g_scale[0] *= scale.x; g_scale[1] *= scale.y; g_scale[2] *= scale.z;
+          const float n = quat_norm(raw_rot);
+          const float dot = g_rot.x * rot.x + g_rot.y * rot.y + g_rot.z * rot.z + g_rot.w * rot.w;
+          const float inv_n = 1.0f / n;
+          // |q| below the clamp: the denominator is the constant eps, no projection term
+          const float pd = (n > 1e-12f) ? dot : 0.f;
+          g_rot = {(g_rot.x - rot.x * pd) * inv_n, (g_rot.y - rot.y * pd) * inv_n,
+                   (g_rot.z - rot.z * pd) * inv_n, (g_rot.w - rot.w * pd) * inv_n};
+        }
+      }
       g_mean2D = dL_dmean2D;
       if (depth_threshold > 0.f) {  // __init__.py:171-185
         const float q = depth / depth_threshold;
@@ -494,7 +511,7 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
       prm.scale_modifier, cov3D_precomp, prm.viewmatrix, prm.projmatrix, focal_x, focal_y,
       prm.tanfovx, prm.tanfovy, prm.campos, accum, prm.depth_threshold, prm.antialiasing != 0,
       dL_dmeans3D, dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
-      dL_drotations, dL_dcov3D, admm);
+      dL_drotations, dL_dcov3D, admm, prm.raw_inputs != 0);
   return check_launch("preprocess_bwd", prm.debug != 0, s);
 }
 

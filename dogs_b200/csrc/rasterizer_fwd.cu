@@ -103,7 +103,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int* __restrict__ radii, SplatRecord* __restrict__ rec,
                       uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
                       uint32_t* __restrict__ depth_key, uint4* __restrict__ emit_rec,
-                      uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing) {
+                      uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing, bool raw_inputs) {
   extern __shared__ float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
   const int first = blockIdx.x * PRE_THREADS;
@@ -150,6 +150,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     } else {
       float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
       float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+      if (raw_inputs) { sc = act_exp3(sc); q = act_normalize(q); }
       cov3d_from_scale_rot(sc, scale_modifier, q, cov3D);
     }
     float3 cov = cov2d_from_cov3d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
@@ -189,7 +190,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     clamped_out[idx] = (uint8_t)clamped;
 
     const float depth = p_view.z;
-    const float opacity = opacities[idx] * h_convolution_scaling;
+    const float opacity = (raw_inputs ? act_sigmoid(opacities[idx]) : opacities[idx]) * h_convolution_scaling;
     radius_out = (int)my_radius;
     const float4 co = {conic.x, conic.y, conic.z, opacity};
     SplatRecord r;
@@ -300,7 +301,7 @@ filter_kernel(int P, const float* __restrict__ means3D, const float* __restrict_
               const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
               const float* __restrict__ proj, int W, int H, float tan_fovx, float tan_fovy,
               float focal_x, float focal_y, int* __restrict__ radii, uint32_t gx, uint32_t gy,
-              bool prefiltered) {
+              bool prefiltered, bool raw_inputs) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P) return;
   int radius_out = 0;
@@ -324,6 +325,7 @@ filter_kernel(int P, const float* __restrict__ means3D, const float* __restrict_
     } else {
       float3 sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
       float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+      if (raw_inputs) { sc = act_exp3(sc); q = act_normalize(q); }
       cov3d_from_scale_rot(sc, scale_modifier, q, cov3D);
     }
     float3 cov = cov2d_from_cov3d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov3D, view);
@@ -376,7 +378,7 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
       prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
       cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
       prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
-      g.emit_rec, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0);
+      g.emit_rec, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0, prm.raw_inputs != 0);
   return check_launch("preprocess_fwd", prm.debug != 0, s);
 }
 
@@ -402,6 +404,25 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_ke
   return check_launch("tile_ranges", prm.debug != 0, s);
 }
 
+__global__ void activations_kernel(int P, const float* __restrict__ raw_op, const float* __restrict__ raw_sc,
+                                   const float* __restrict__ raw_rot, float* __restrict__ op,
+                                   float* __restrict__ sc, float* __restrict__ rot) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  if (raw_op) op[idx] = act_sigmoid(raw_op[idx]);
+  if (raw_sc) {
+    const float3 s = act_exp3({raw_sc[3 * idx], raw_sc[3 * idx + 1], raw_sc[3 * idx + 2]});
+    sc[3 * idx] = s.x; sc[3 * idx + 1] = s.y; sc[3 * idx + 2] = s.z;
+  }
+  if (raw_rot) reinterpret_cast<float4*>(rot)[idx] = act_normalize(reinterpret_cast<const float4*>(raw_rot)[idx]);
+}
+
+int launch_activations(int P, const float* raw_op, const float* raw_sc, const float* raw_rot, float* op,
+                       float* sc, float* rot, cudaStream_t s) {
+  activations_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, raw_op, raw_sc, raw_rot, op, sc, rot);
+  return check_launch("activations", false, s);
+}
+
 int launch_filter(const DgrParams& prm, const float* means3D, const float* scales,
                   const float* rotations, const float* cov3D_precomp, int32_t* radii,
                   cudaStream_t s) {
@@ -411,7 +432,7 @@ int launch_filter(const DgrParams& prm, const float* means3D, const float* scale
   filter_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(
       prm.P, means3D, scales, prm.scale_modifier, rotations, cov3D_precomp, prm.viewmatrix,
       prm.projmatrix, prm.W, prm.H, prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, gx, gy,
-      prm.prefiltered != 0);
+      prm.prefiltered != 0, prm.raw_inputs != 0);
   return check_launch("visible_filter", prm.debug != 0, s);
 }
 

@@ -40,6 +40,11 @@ class GaussianRasterizationSettings(NamedTuple):  # reference __init__.py:203-21
     antialiasing: bool = False
     depth_threshold: float = 0.0
     f_count: bool = False       # LightGaussian importance statistics (old rasterizer's count mode)
+    # Extension: opacities / scales / rotations passed to the rasterizer are the model's
+    # raw parameters (_opacity, _scaling, _quaternion); sigmoid / exp / F.normalize
+    # (gaussian_splat_model.py:148-153) run inside preprocess and the returned gradients are w.r.t. the
+    # raw tensors, replacing three torch activation kernels and their three backward kernels per render.
+    raw_activations: bool = False
 
 
 def cpu_deep_copy_tuple(input_tuple):
@@ -69,7 +74,8 @@ def _params(rs, P, M, device, backward=False):
         prefiltered=int(bool(rs.prefiltered)), antialiasing=int(bool(rs.antialiasing)),
         debug=int(bool(rs.debug)),
         bg=keep[0].data_ptr(), viewmatrix=keep[1].data_ptr(), projmatrix=keep[2].data_ptr(),
-        campos=keep[3].data_ptr(), ref_bucket_cull_quirk=int(bool(REFERENCE_BACKWARD_QUIRK)))
+        campos=keep[3].data_ptr(), ref_bucket_cull_quirk=int(bool(REFERENCE_BACKWARD_QUIRK)),
+        raw_inputs=int(bool(getattr(rs, "raw_activations", False))))
     blk = _FUSED_ADMM
     if backward and blk is not None:
         zx, zd, zs = blk.zmu[0], blk.zmu[1], blk.zmu[2]

@@ -67,6 +67,11 @@ typedef struct DgrParams {
       instantiated 1-D on a 16x16 block (forward.cu:495-500), which only reduces the tile's first
       warp (pixel rows 0-1), so PerGaussianRenderCUDA (backward.cu:505-507) drops every 32-splat
       bucket starting at or after max(n_contrib of rows 0-1).  See DESIGN.md "Reference defect". */
+  int32_t raw_inputs;      /* !=0: opacities / scales / rotations are the model's RAW parameters.  The
+      activations the reference applies in torch before every render (gaussian_splat_model.py:148-153,
+      179,202,259: sigmoid, exp, F.normalize) run on load inside preprocess / visible_filter, and
+      dgr_backward returns gradients w.r.t. the raw tensors.  scales/rotations only
+      when cov3D_precomp is null; opacity always. */
   const DgrAdmmPenalty* admm;    /* backward only, host pointer, nullable (see DgrAdmmPenalty) */
   /* forward only, nullable device pointers: LightGaussian importance statistics (count mode of the
    * reference's older rasterizer, old_diff-gaussian-rasterization/cuda_rasterizer/forward.cu:400-513,
@@ -138,6 +143,14 @@ int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* 
 /* mark_visible (rasterize_points.cu:254-272). present: [P] bytes (bool). */
 int dgr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
+
+/* The activations of DgrParams::raw_inputs as a stand-alone pass (gaussian_splat_model.py:148-153:
+ * get_opacity = sigmoid(_opacity), get_scaling = exp(_scaling), get_quaternion = F.normalize(_quaternion)),
+ * bit-identical to what preprocess applies and to the torch kernels; for callers that need the
+ * activated values themselves (export, densification statistics).  Any of the three pairs may be null. */
+int dgr_apply_activations(int32_t P, const float* raw_opacities, const float* raw_scales,
+                          const float* raw_rotations, float* opacities, float* scales,
+                          float* rotations, void* stream);
 
 /* Introspection used by the parity tests (compare stage by stage with the reference's
  * opaque buffers).  Offsets in bytes inside the geom / binning / image buffers. */

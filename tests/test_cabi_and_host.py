@@ -34,10 +34,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from dogs_b200 import _lib
-    # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 1 int (+ padding to 8), 1 pointer
+    # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 2 ints, 1 pointer, 2 pointers
     assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16
     assert _lib.DgrParams.bg.offset == 48 and _lib.DgrParams.ref_bucket_cull_quirk.offset == 80
-    assert _lib.DgrParams.admm.offset == 88
+    assert _lib.DgrParams.raw_inputs.offset == 84 and _lib.DgrParams.admm.offset == 88
     assert C.sizeof(_lib.DgrAdmmPenalty) == 3 * 8 + 3 * 4 + 4 + 8
     assert C.sizeof(_lib.DgrLayout) == 11 * 8
     assert C.sizeof(_lib.AdmmTensors) == 48
@@ -96,7 +96,10 @@ def test_settings_fields_match_reference_api():
     import dogs_b200.diff_gaussian_rasterization as dgr
     assert dgr.GaussianRasterizationSettings._fields == (
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
-        "sh_degree", "campos", "prefiltered", "debug", "antialiasing", "depth_threshold", "f_count")
+        "sh_degree", "campos", "prefiltered", "debug", "antialiasing", "depth_threshold", "f_count",
+        "raw_activations")
+    # the reference's 14 fields come first and in its order; the extensions are defaulted
+    assert dgr.GaussianRasterizationSettings._field_defaults["raw_activations"] is False
     import inspect
     sig = inspect.signature(dgr.GaussianRasterizer.forward)
     assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "dc", "shs", "colors_precomp", "scales",
