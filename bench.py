@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--cfg", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused-loss", action="store_true",
+                    help="ours: evaluate the loss with torch ops around fused_ssim, as the reference's trainer does")
     ap.add_argument("--no-clocks", action="store_true", help="do not query NVML inside the timed region")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3)
@@ -232,7 +234,13 @@ def main():
         admm = A.AdmmBlock(x, plan)                  # penalty gradients accumulate into the leaves' .grad
         admm.fuse_into_rasterizer(True)              # xyz / f_dc / f_rest penalty fused into the rasterizer backward
 
+    fused_loss = None
+    if args.impl == "ours" and not args.unfused_loss:
+        from dogs_b200.fused_ssim import fused_l1_ssim_loss as fused_loss   # same loss, 2 launches
+
     def loss_of(img, tgt):
+        if fused_loss is not None:
+            return fused_loss(img, tgt, 0.2)
         l1 = (img - tgt).abs().mean()
         return 0.8 * l1 + 0.2 * (1.0 - fused_ssim(img[None], tgt[None]))
 
@@ -376,6 +384,8 @@ def main():
                                    f"0.8*L1+0.2*(1-SSIM) + bwd" + (", ADMM penalty/iter + 1 consensus round per "
                                    f"{K} iters, one block per GPU" if distributed else ""),
                        "l2_policy": "inputs (708 MB of Gaussian parameters + 10 M instance lists) exceed the 126 MB L2",
+                       "loss": ("fused_l1_ssim_loss (one launch forward, one backward)" if fused_loss is not None
+                                else "torch L1 ops + fused_ssim"),
                        "blocks": world if args.impl == "ours" else 1},
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "step_ms": {"min": per_step[0], "median": per_step[K // 2], "max": per_step[-1]},

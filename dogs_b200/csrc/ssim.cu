@@ -26,11 +26,19 @@ __device__ __forceinline__ float pix_or_zero(const float* __restrict__ plane, in
   return (x >= W || y >= H || x < 0 || y < 0) ? 0.0f : plane[(size_t)y * W + x];
 }
 
+// Workspace of the fused photometric loss: running sums + a ticket counter.  Zero-initialised once by
+// the caller; the last CTA of every launch folds the sums into the loss and zeroes it again.
+struct LossWorkspace { double sum_l1, sum_ssim; unsigned int ticket; unsigned int pad; };
+
+// LOSS = true: instead of the SSIM map the kernel produces the scalar training loss of
+// gaussian_trainer.py:403-405, (1-lambda) * mean|img1-img2| + lambda * (1 - mean SSIM), in one launch.
+template <bool LOSS>
 __global__ void __launch_bounds__(SS_THREADS)
 fssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img1,
                  const float* __restrict__ img2, float* __restrict__ ssim_map,
                  float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
-                 float* __restrict__ dm_dsigma12) {
+                 float* __restrict__ dm_dsigma12, LossWorkspace* __restrict__ ws, float lambda,
+                 double inv_count, float* __restrict__ loss_out) {
   __shared__ float p1[SS_SY][SS_PAD];
   __shared__ float p2[SS_SY][SS_PAD];
   __shared__ float xc[5][SS_SY][SS_BX];
@@ -63,6 +71,7 @@ fssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img
   __syncthreads();
   const int lx = tid & 31;
   const int px = blockIdx.x * SS_BX + lx;
+  float acc_l1 = 0.f, acc_m = 0.f;
 #pragma unroll
   for (int r = 0; r < SS_BY / (SS_THREADS / 32); r++) {
     const int ly = (tid >> 5) + r * (SS_THREADS / 32);
@@ -90,7 +99,12 @@ fssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img
     const float m = (C * D) / (A * B);
     if (px < W && py < H) {
       const size_t gi = plane + (size_t)py * W + px;
-      ssim_map[gi] = m;
+      if (LOSS) {
+        acc_m += m;
+        acc_l1 += fabsf(p1[ly + SS_R][lx + SS_R] - p2[ly + SS_R][lx + SS_R]);
+      } else {
+        ssim_map[gi] = m;
+      }
       if (dm_dmu1) {
         dm_dmu1[gi] = ((mu2 * 2.0f * D) / (A * B) - (mu2 * 2.0f * C) / (A * B) -
                        (mu1 * 2.0f * C * D) / (A * A * B) + (mu1 * 2.0f * C * D) / (A * B * B));
@@ -99,13 +113,46 @@ fssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img
       }
     }
   }
+  if (LOSS) {
+    __shared__ double red[2][SS_THREADS / 32];
+    double dl1 = acc_l1, dm = acc_m;   // <= 4 pixels per thread in float, everything above in double
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dl1 += __shfl_xor_sync(0xffffffffu, dl1, o);
+      dm += __shfl_xor_sync(0xffffffffu, dm, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = dl1; red[1][tid >> 5] = dm; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int w = 0; w < SS_THREADS / 32; w++) { a += red[0][w]; b += red[1][w]; }
+      atomicAdd(&ws->sum_l1, a);
+      atomicAdd(&ws->sum_ssim, b);
+      __threadfence();
+      const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+      if (atomicAdd(&ws->ticket, 1u) == total - 1) {   // last CTA: every partial sum is visible
+        __threadfence();
+        const double s_l1 = *reinterpret_cast<volatile double*>(&ws->sum_l1);
+        const double s_m = *reinterpret_cast<volatile double*>(&ws->sum_ssim);
+        *loss_out = (float)((1.0 - (double)lambda) * (s_l1 * inv_count) + (double)lambda * (1.0 - s_m * inv_count));
+        ws->sum_l1 = 0.0; ws->sum_ssim = 0.0; ws->ticket = 0u;   // ready for the next launch
+      }
+    }
+  }
 }
 
+// LOSS = true: backward of the fused photometric loss.  dL/dmap is the constant w_ssim (= -lambda/N)
+// and the L1 term w_l1 * sign(img1 - img2) (= (1-lambda)/N * sgn) is added to the same store; both are
+// scaled by the upstream scalar *grad_loss when it is given.
+template <bool LOSS>
 __global__ void __launch_bounds__(SS_THREADS)
 fssim_bwd_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
                  const float* __restrict__ dL_dmap, const float* __restrict__ dm_dmu1,
                  const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
-                 float* __restrict__ dL_dimg1) {
+                 float* __restrict__ dL_dimg1, float w_ssim, float w_l1,
+                 const float* __restrict__ grad_loss) {
+  if (LOSS && grad_loss) { const float g = *grad_loss; w_ssim *= g; w_l1 *= g; }
   __shared__ float t1[SS_SY][SS_PAD];
   __shared__ float t2[SS_SY][SS_PAD];
   __shared__ float t3[SS_SY][SS_PAD];
@@ -119,7 +166,7 @@ fssim_bwd_kernel(int H, int W, const float* __restrict__ img1, const float* __re
     float dl = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
     if (!(x >= W || y >= H || x < 0 || y < 0)) {
       const size_t gi = plane + (size_t)y * W + x;
-      dl = dL_dmap[gi]; m1 = dm_dmu1[gi]; m2 = dm_dsigma1_sq[gi]; m3 = dm_dsigma12[gi];
+      dl = LOSS ? w_ssim : dL_dmap[gi]; m1 = dm_dmu1[gi]; m2 = dm_dsigma1_sq[gi]; m3 = dm_dsigma12[gi];
     }
     t1[ly][lx] = m1 * dl;
     t2[ly][lx] = m2 * dl;
@@ -160,6 +207,10 @@ fssim_bwd_kernel(int H, int W, const float* __restrict__ img1, const float* __re
       dL_dpix += q[0];
       dL_dpix += pix1 * 2.0f * q[1];
       dL_dpix += pix2 * q[2];
+      if (LOSS) {   // + (1-lambda)/N * sgn(img1 - img2), as autograd sums the two branches
+        const float d = pix1 - pix2;
+        dL_dpix += d > 0.f ? w_l1 : (d < 0.f ? -w_l1 : 0.f);
+      }
       dL_dimg1[gi] = dL_dpix;
     }
   }
@@ -181,8 +232,8 @@ extern "C" int fssim_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float 
   }
   if ((long long)B * CH > 65535) { set_error("fssim_forward: B*CH > 65535"); return 1; }
   dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
-  fssim_fwd_kernel<<<grid, SS_THREADS, 0, s>>>(H, W, C1, C2, img1, img2, ssim_map, dm_dmu1,
-                                               dm_dsigma1_sq, dm_dsigma12);
+  fssim_fwd_kernel<false><<<grid, SS_THREADS, 0, s>>>(H, W, C1, C2, img1, img2, ssim_map, dm_dmu1,
+                                                      dm_dsigma1_sq, dm_dsigma12, nullptr, 0.f, 0.0, nullptr);
   return check_launch("fssim_forward", false, s);
 }
 
@@ -199,7 +250,44 @@ extern "C" int fssim_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float
   }
   if ((long long)B * CH > 65535) { set_error("fssim_backward: B*CH > 65535"); return 1; }
   dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
-  fssim_bwd_kernel<<<grid, SS_THREADS, 0, s>>>(H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq,
-                                               dm_dsigma12, dL_dimg1);
+  fssim_bwd_kernel<false><<<grid, SS_THREADS, 0, s>>>(H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq,
+                                                      dm_dsigma12, dL_dimg1, 0.f, 0.f, nullptr);
   return check_launch("fssim_backward", false, s);
+}
+
+extern "C" int fssim_l1_loss_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                                     float lambda_dssim, const float* img1, const float* img2,
+                                     float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12,
+                                     void* workspace, float* loss_out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || CH <= 0 || H <= 0 || W <= 0) { set_error("fssim_l1_loss_forward: empty image"); return 1; }
+  if (!img1 || !img2 || !workspace || !loss_out) { set_error("fssim_l1_loss_forward: null pointer"); return 1; }
+  if ((dm_dmu1 == nullptr) != (dm_dsigma1_sq == nullptr) || (dm_dmu1 == nullptr) != (dm_dsigma12 == nullptr)) {
+    set_error("fssim_l1_loss_forward: pass all three derivative maps or none");
+    return 1;
+  }
+  if ((long long)B * CH > 65535) { set_error("fssim_l1_loss_forward: B*CH > 65535"); return 1; }
+  dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
+  const double inv_count = 1.0 / ((double)B * CH * H * W);
+  fssim_fwd_kernel<true><<<grid, SS_THREADS, 0, s>>>(H, W, C1, C2, img1, img2, nullptr, dm_dmu1, dm_dsigma1_sq,
+                                                     dm_dsigma12, (LossWorkspace*)workspace, lambda_dssim,
+                                                     inv_count, loss_out);
+  return check_launch("fssim_l1_loss_forward", false, s);
+}
+
+extern "C" int fssim_l1_loss_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float w_ssim, float w_l1,
+                                      const float* img1, const float* img2, const float* dm_dmu1,
+                                      const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                                      const float* grad_loss, float* dL_dimg1, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || CH <= 0 || H <= 0 || W <= 0) return 0;
+  if (!img1 || !img2 || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) {
+    set_error("fssim_l1_loss_backward: null pointer");
+    return 1;
+  }
+  if ((long long)B * CH > 65535) { set_error("fssim_l1_loss_backward: B*CH > 65535"); return 1; }
+  dim3 grid((W + SS_BX - 1) / SS_BX, (H + SS_BY - 1) / SS_BY, B * CH);
+  fssim_bwd_kernel<true><<<grid, SS_THREADS, 0, s>>>(H, W, img1, img2, nullptr, dm_dmu1, dm_dsigma1_sq,
+                                                     dm_dsigma12, dL_dimg1, w_ssim, w_l1, grad_loss);
+  return check_launch("fssim_l1_loss_backward", false, s);
 }

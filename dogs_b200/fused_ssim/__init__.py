@@ -85,3 +85,64 @@ def fused_ssim(img1, img2, padding="same", train=True):
     if padding not in allowed_padding:
         raise AssertionError(f"padding must be one of {allowed_padding}")
     return FusedSSIMMap.apply(_C1, _C2, img1, img2, padding, train).mean()
+
+
+# ---- fused photometric loss (extension) ----------------------------------------------------------
+_loss_ws = {}   # (device, stream) -> 32-byte workspace, zeroed once; the kernel hands it back zeroed
+
+
+def _workspace(device):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        ws = _loss_ws[key] = torch.zeros(4, dtype=torch.float64, device=device)
+    return ws
+
+
+class _L1SSIMLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2, lambda_dssim):
+        img1, img2 = _check_pair(img1, img2)
+        if img1.numel() == 0:
+            raise RuntimeError("fused_l1_ssim_loss: empty image")
+        B, CH, H, W = img1.shape
+        train = ctx.needs_input_grad[0]
+        maps = [torch.empty_like(img1) for _ in range(3)] if train else [None] * 3
+        loss = torch.empty((), dtype=torch.float32, device=img1.device)
+        with torch.cuda.device(img1.device):
+            L.check(L.lib().fssim_l1_loss_forward(B, CH, H, W, _C1, _C2, float(lambda_dssim), img1.data_ptr(),
+                                                  img2.data_ptr(), L.ptr(maps[0]), L.ptr(maps[1]), L.ptr(maps[2]),
+                                                  _workspace(img1.device).data_ptr(), loss.data_ptr(),
+                                                  L.stream_ptr(img1.device)))
+        if train:
+            ctx.save_for_backward(img1.detach(), img2, *maps)
+        ctx.lambda_dssim = float(lambda_dssim)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        img1, img2, *maps = ctx.saved_tensors
+        B, CH, H, W = img1.shape
+        # the per-pixel weights autograd would produce in float32: (-lambda) / N and (1 - lambda) / N
+        n = torch.tensor(float(img1.numel()), dtype=torch.float32)
+        lam = torch.tensor(ctx.lambda_dssim, dtype=torch.float32)
+        w_ssim = float(-lam / n)
+        w_l1 = float((1.0 - lam) / n)
+        grad_loss = L.require_cuda(grad_loss, "grad_loss")
+        grad = torch.empty_like(img1)
+        with torch.cuda.device(img1.device):
+            L.check(L.lib().fssim_l1_loss_backward(B, CH, H, W, w_ssim, w_l1, img1.data_ptr(), img2.data_ptr(),
+                                                   maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(),
+                                                   grad_loss.data_ptr(), grad.data_ptr(),
+                                                   L.stream_ptr(img1.device)))
+        return grad, None, None
+
+
+def fused_l1_ssim_loss(img1, img2, lambda_dssim=0.2):
+    """(1 - lambda) * l1_loss(img1, img2) + lambda * (1 - fused_ssim(img1, img2)) — the photometric loss
+    of conerf/trainers/gaussian_trainer.py:403-405 — in one forward and one backward launch instead of
+    fused_ssim's two plus ~20 torch elementwise / reduction kernels.  img1, img2: [B,CH,H,W] or [CH,H,W]
+    float32 CUDA; only img1 receives a gradient.  Returns a 0-d tensor."""
+    if img1.dim() == 3:
+        img1, img2 = img1[None], img2[None]
+    return _L1SSIMLoss.apply(img1, img2, lambda_dssim)

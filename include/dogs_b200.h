@@ -193,6 +193,23 @@ int fssim_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float 
                    const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12,
                    float* dL_dimg1, void* stream);
 
+/* Fused photometric loss of the training step (conerf/trainers/gaussian_trainer.py:403-405):
+ *   loss = (1 - lambda) * mean|img1 - img2| + lambda * (1 - mean SSIM(img1, img2)),
+ * which the reference evaluates with ~20 torch elementwise/reduction launches around fused_ssim.
+ * forward: ONE launch; writes the three derivative maps for the backward (NULL = inference) and the
+ *   scalar loss_out (device).  workspace: 32 bytes of device memory, zeroed once by the caller; the
+ *   kernel leaves it zeroed (one workspace per stream).
+ * backward: ONE launch; dL_dimg1 = grad_loss * (w_ssim * dSSIMsum/dimg1 + w_l1 * sign(img1 - img2)) with
+ *   w_ssim = -lambda/N, w_l1 = (1-lambda)/N, N = B*CH*H*W; grad_loss: device scalar, NULL = 1. */
+int fssim_l1_loss_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,
+                          float lambda_dssim, const float* img1, const float* img2,
+                          float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12,
+                          void* workspace, float* loss_out, void* stream);
+int fssim_l1_loss_backward(int32_t B, int32_t CH, int32_t H, int32_t W, float w_ssim, float w_l1,
+                           const float* img1, const float* img2, const float* dm_dmu1,
+                           const float* dm_dsigma1_sq, const float* dm_dsigma12,
+                           const float* grad_loss, float* dL_dimg1, void* stream);
+
 /* ---- simple-knn distCUDA2 (submodules/simple-knn/spatial.cu:17-35) --------------- */
 int sknn_dist2(int32_t P, const float* points, float* mean_dist2,
                dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
