@@ -86,6 +86,8 @@ __device__ __forceinline__ V3 color_from_sh(int deg, V3 pos, V3 campos, V3 dc, c
   return {fmaxf(result.x, 0.0f), fmaxf(result.y, 0.0f), fmaxf(result.z, 0.0f)};
 }
 
+constexpr int COOP_RECT_TILES = 16;   // rects with more tiles than this are walked by the whole warp
+
 // One thread per Gaussian.  The CTA's slice of the SH tensor (the bulk of the input bytes:
 // 180 of 236 B per Gaussian) is contiguous, so it is staged into shared memory with coalesced
 // 16-byte loads and read back row-wise at a stride of 3*M floats (odd => conflict-free).
@@ -129,7 +131,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   uint32_t ntiles = 0, dkey = 0xffffffffu;
   unsigned long long mask = 0ull;
   uint32_t rect_word = 0;
-  // set by lanes whose rect has more than 32 tiles: the warp walks those rects together
+  // set by lanes whose rect has more than COOP_RECT_TILES tiles: the warp walks those rects together
   float4 big_co = {0.f, 0.f, 0.f, 0.f};
   float2 big_xy = {0.f, 0.f};
   float big_thr = 0.f;
@@ -211,7 +213,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64 && rect_min.x < 2048u && rect_min.y < 2048u;
     rect_word = small ? (rect_min.x | (rect_min.y << 11) | ((uint32_t)rw << 22)) : 0u;   // mask fits 64 bits
     const int ntot = rw * (int)(rect_max.y - rect_min.y);
-    if (ntot > 32) {
+    if (ntot > COOP_RECT_TILES) {
       big_co = co; big_xy = point_image; big_thr = thr;
       big_x0 = rect_min.x; big_y0 = rect_min.y; big_w = rw; big_n = ntot;
     } else {
@@ -224,7 +226,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     }
     dkey = __float_as_uint(depth);
   } while (0);
-  // Rects of more than 32 tiles (0.3 % of the Gaussians at C3, up to ~1000 tiles each) are walked by
+  // Large rects (a few per cent of the Gaussians at C3, the largest ~1000 tiles) are walked by
   // the whole warp, 32 tiles per step: one thread looping over such a rect alone took longer than the
   // rest of the grid together (ncu: SMs idle behind a handful of 100-us threads).
   {
