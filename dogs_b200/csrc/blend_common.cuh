@@ -19,7 +19,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // entry per lane, whether the entry can reach alpha >= 1/255 anywhere in ITS block; only those
 // entries enter the per-pixel loop.  The test is conservative — the exact minimum of the quadratic
 // form 0.5*d^T C d over the block's pixel-centre rectangle (convex => attained at the mean if it
-// lies inside, otherwise on one of the four edges), compared with thr = ln(255*opacity) plus a
+// lies inside, otherwise on an edge facing the mean), compared with thr = ln(255*opacity) plus a
 // margin that dwarfs the rounding error — so a skipped entry has alpha < 1/255 at every pixel of
 // the block and skipping it cannot change any result.
 __device__ __forceinline__ float quad_form(float a, float b, float c, float dx, float dy) {
@@ -27,27 +27,18 @@ __device__ __forceinline__ float quad_form(float a, float b, float c, float dx, 
 }
 __device__ __forceinline__ bool block_reachable(const float4 co, float mx, float my, float x0,
                                                 float y0, float x1, float y1, float thr) {
+  // The clamped mean is the point of the rectangle's facing edge(s).  The form grows along every ray
+  // from the mean, and a ray to any point of a far edge first crosses a facing edge, so only the (at
+  // most two) edges facing the mean can hold the minimum.
   const float cxp = fminf(fmaxf(mx, x0), x1), cyp = fminf(fmaxf(my, y0), y1);
-  float best;
-  if (cxp == mx && cyp == my) {
-    best = 0.f;                                   // mean inside the rectangle
-  } else {
-    const float ia = __frcp_rn(co.x), ic = __frcp_rn(co.z);
-    // horizontal edges: minimise over x for fixed dy
-    float dy = y0 - my;
-    float dx = fminf(fmaxf(mx - co.y * dy * ia, x0), x1) - mx;
-    best = quad_form(co.x, co.y, co.z, dx, dy);
-    dy = y1 - my;
-    dx = fminf(fmaxf(mx - co.y * dy * ia, x0), x1) - mx;
-    best = fminf(best, quad_form(co.x, co.y, co.z, dx, dy));
-    // vertical edges: minimise over y for fixed dx
-    dx = x0 - mx;
-    dy = fminf(fmaxf(my - co.y * dx * ic, y0), y1) - my;
-    best = fminf(best, quad_form(co.x, co.y, co.z, dx, dy));
-    dx = x1 - mx;
-    dy = fminf(fmaxf(my - co.y * dx * ic, y0), y1) - my;
-    best = fminf(best, quad_form(co.x, co.y, co.z, dx, dy));
-  }
+  const float ex = cxp - mx, ey = cyp - my;          // 0 when the mean is inside that range
+  // vertical facing edge x = cxp: minimise over y;  horizontal facing edge y = cyp: minimise over x
+  const float dyv = fminf(fmaxf(my - co.y * ex * __frcp_rn(co.z), y0), y1) - my;
+  const float dxh = fminf(fmaxf(mx - co.y * ey * __frcp_rn(co.x), x0), x1) - mx;
+  const float qv = quad_form(co.x, co.y, co.z, ex, dyv);
+  const float qh = quad_form(co.x, co.y, co.z, dxh, ey);
+  // mean inside the x range: only the horizontal edge counts (and vice versa); inside both: 0
+  float best = (ex != 0.f) ? ((ey != 0.f) ? fminf(qv, qh) : qv) : ((ey != 0.f) ? qh : 0.f);
   // !(best > ...) keeps NaNs on the safe (processed) side
   return !(best > thr + 0.01f + 1e-5f * fabsf(thr));
 }
