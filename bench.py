@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--cfg", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-admm", action="store_true",
+                    help="profiling aid: run the per-iteration ADMM work of the N>1 path on one GPU (virtual neighbour blocks)")
     ap.add_argument("--unfused-loss", action="store_true",
                     help="ours: evaluate the loss with torch ops around fused_ssim, as the reference's trainer does")
     ap.add_argument("--no-clocks", action="store_true", help="do not query NVML inside the timed region")
@@ -221,7 +223,7 @@ def main():
         return d
 
     admm = None
-    if distributed:
+    if distributed or args.force_admm:
         # ADMM block state: 1-D chain of blocks, 24.5 % of a block shared with each neighbour (~49 % shared,
         # SURVEY.md 8d C4/C5).  The consensus variables are the 6 parameter tensors of the block.
         from dogs_b200 import admm as A
@@ -229,10 +231,20 @@ def main():
         stride = P - ov
         gidx = torch.arange(P, dtype=torch.int64) + rank * stride
         n_global = stride * (world - 1) + P
-        plan = A.build_plan(gidx.to(dev), n_global).to(dev)
+        if args.force_admm and not distributed:
+            # one GPU: pretend two neighbour blocks exist so that the same ~49 % of the block is shared
+            n_global = P
+            count = torch.ones(P, dtype=torch.int32)
+            count[:ov] = 2
+            count[-ov:] = 2
+            plan = A.ConsensusPlan(gidx, count).to(dev)
+        else:
+            plan = A.build_plan(gidx.to(dev), n_global).to(dev)
         x = [leaves[k] for k in ("means3D", "dc", "sh", "scales", "rotations", "opacities")]
         admm = A.AdmmBlock(x, plan)                  # penalty gradients accumulate into the leaves' .grad
-        admm.fuse_into_rasterizer(True)              # xyz / f_dc / f_rest penalty fused into the rasterizer backward
+        # the six leaf tensors fed to the rasterizer are the consensus variables themselves, so the whole
+        # penalty (all 59 floats per Gaussian) is added by the rasterizer backward
+        admm.fuse_into_rasterizer(True, all_groups=True)
 
     fused_loss = None
     if args.impl == "ours" and not args.unfused_loss:

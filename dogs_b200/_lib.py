@@ -16,7 +16,9 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 class DgrAdmmPenalty(C.Structure):
     _fields_ = [("zmu_xyz", C.c_void_p), ("zmu_dc", C.c_void_p), ("zmu_sh", C.c_void_p),
+                ("zmu_scale", C.c_void_p), ("zmu_rot", C.c_void_p), ("zmu_opacity", C.c_void_p),
                 ("coef_xyz", C.c_float), ("coef_dc", C.c_float), ("coef_sh", C.c_float),
+                ("coef_scale", C.c_float), ("coef_rot", C.c_float), ("coef_opacity", C.c_float),
                 ("sums", C.c_void_p)]
 
 

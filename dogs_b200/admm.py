@@ -146,8 +146,9 @@ class AdmmBlock:
         self.buf = torch.zeros(max(plan.S_total, 1) * ROW, dtype=torch.float32, device=dev)
         self.residuals = torch.zeros(12, dtype=torch.float64, device=dev)
         self.pen_sums = torch.zeros(6, dtype=torch.float64, device=dev)
-        self.fused_sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.fused_sums = torch.zeros(6, dtype=torch.float64, device=dev)
         self.fused = False
+        self.fused_all = False
         self._pen_scale, self._pen_scale_key = None, None
         self.last_primal: Optional[List[float]] = None
         self.last_dual: Optional[List[float]] = None
@@ -187,15 +188,19 @@ class AdmmBlock:
 
     def fused_coef(self):
         n = self.plan.n_local
-        return [self.rho[g] / max(n * GROUP_SIZES[g], 1) for g in range(3)]
+        return [self.rho[g] / max(n * GROUP_SIZES[g], 1) for g in range(6)]
 
-    def fuse_into_rasterizer(self, enable: bool = True):
+    def fuse_into_rasterizer(self, enable: bool = True, all_groups: bool = False):
         """Let the rasterizer backward add the penalty gradient of xyz / f_dc / f_rest (51 of the 59
         floats) while it writes those gradients anyway (DgrAdmmPenalty); add_penalty_grads_ then only
         touches scaling / quaternion / opacity.  Valid when the rasterizer is fed this block's raw
-        xyz, f_dc and f_rest tensors (conerf's render() does)."""
+        xyz, f_dc and f_rest tensors (conerf's render() does).
+        all_groups=True also fuses scaling / quaternion / opacity: valid when the rasterizer receives
+        the consensus (raw) tensors themselves, i.e. GaussianRasterizationSettings.raw_activations;
+        add_penalty_grads_ then launches no penalty kernel at all."""
         from . import diff_gaussian_rasterization as dgr
         self.fused = bool(enable)
+        self.fused_all = bool(enable and all_groups)
         dgr.set_fused_admm(self if enable else None)
         self.fused_sums.zero_()
 
@@ -209,14 +214,18 @@ class AdmmBlock:
         for t in self.x:
             if t.grad is None:
                 t.grad = torch.zeros_like(t)
-        self.pen_sums.zero_()
         xs = [t.detach() for t in self.x]
-        if self.fused:   # groups 0-2 were handled by the rasterizer backward of this iteration
-            xs = [None, None, None] + xs[3:]
-        self.ops.penalty(xs, None, self.zmu, [t.grad for t in self.x], n, coef, self.pen_sums)
-        if self.fused:
-            self.pen_sums[:3] += self.fused_sums
+        if self.fused_all:   # every group was handled by the rasterizer backward of this iteration
+            self.pen_sums.copy_(self.fused_sums)
             self.fused_sums.zero_()
+        else:
+            self.pen_sums.zero_()
+            if self.fused:   # groups 0-2 were handled by the rasterizer backward of this iteration
+                xs = [None, None, None] + xs[3:]
+            self.ops.penalty(xs, None, self.zmu, [t.grad for t in self.x], n, coef, self.pen_sums)
+            if self.fused:
+                self.pen_sums[:3] += self.fused_sums[:3]
+                self.fused_sums.zero_()
         # penalties_g = 0.5 * rho_g/numel_g * sum r^2; the scale vector lives on the device and is only
         # rebuilt when rho changes (no host->device copy, no sync, in the per-iteration path)
         key = tuple(coef)

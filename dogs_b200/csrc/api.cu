@@ -257,8 +257,11 @@ static int backward_impl(const DgrParams* prm, int32_t num_rendered, const float
   GeomState g = GeomState::carve(const_cast<char*>(geom), P);
   BinState b = BinState::carve(const_cast<char*>(binning), (size_t)num_rendered);
   ImgState im = ImgState::carve(const_cast<char*>(image), N, T);
-  float* accum = reinterpret_cast<float*>(scratch_alloc(scratch_user, bwd_accum_bytes(P)));
+  const bool pen_sums = p.admm && p.admm->zmu_xyz && p.admm->sums;
+  float* accum = reinterpret_cast<float*>(
+      scratch_alloc(scratch_user, bwd_accum_bytes(P) + (pen_sums ? bwd_penalty_partial_bytes(P) : 0)));
   if (!accum) { set_error("backward: scratch allocation failed"); return 1; }
+  double* pen_partial = pen_sums ? reinterpret_cast<double*>(reinterpret_cast<char*>(accum) + bwd_accum_bytes(P)) : nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   if (stage_ms) {
     for (auto& e : ev) cudaEventCreate(&e);
@@ -271,7 +274,7 @@ static int backward_impl(const DgrParams* prm, int32_t num_rendered, const float
                                  g, accum, dL_dmeans3D, dL_dmeans2D, sh_path ? dL_ddc : nullptr,
                                  sh_path ? dL_dsh : nullptr, dL_dcolors_precomp, dL_dopacity,
                                  cov3D_precomp ? nullptr : dL_dscales,
-                                 cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, s);
+                                 cov3D_precomp ? nullptr : dL_drotations, dL_dcov3D, pen_partial, s);
   if (stage_ms) {
     cudaEventRecord(ev[2], s);
     cudaEventSynchronize(ev[2]);

@@ -233,6 +233,8 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
                           const GeomState& g, const float* accum, float* dL_dmeans3D,
                           float* dL_dmeans2D, float* dL_ddc, float* dL_dsh,
                           float* dL_dcolors_precomp, float* dL_dopacity, float* dL_dscales,
-                          float* dL_drotations, float* dL_dcov3D, cudaStream_t s);
+                          float* dL_drotations, float* dL_dcov3D, double* pen_partial,
+                          cudaStream_t s);
+size_t bwd_penalty_partial_bytes(size_t P);   // per-CTA partial penalty sums (DgrAdmmPenalty::sums)
 
 }  // namespace dogs

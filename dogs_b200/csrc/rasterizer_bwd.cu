@@ -168,7 +168,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       float* __restrict__ dL_ddc, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dcolors_precomp, float* __restrict__ dL_dopacity_out,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drots,
-                      float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm, bool raw_inputs) {
+                      float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm, bool raw_inputs,
+                      double* __restrict__ pen_partial) {
   extern __shared__ float4 stage4[];
   float* stage = reinterpret_cast<float*>(stage4);
   const int first = blockIdx.x * PREB_THREADS;
@@ -191,7 +192,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     __syncthreads();
   }
 
-  double pen_xyz = 0.0, pen_dc = 0.0, pen_sh = 0.0;
+  double pen_xyz = 0.0, pen_dc = 0.0, pen_sh = 0.0, pen_scale = 0.0, pen_rot = 0.0, pen_op = 0.0;
   if (idx < P) {
     float* sh_row = stage + (size_t)threadIdx.x * 3 * M;
     float3 g_mean3D = {0.f, 0.f, 0.f};
@@ -416,6 +417,26 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         g_dc.x += admm.coef_dc * q0; g_dc.y += admm.coef_dc * q1; g_dc.z += admm.coef_dc * q2;
         pen_dc = (double)(q0 * q0 + q1 * q1 + q2 * q2);
       }
+      // the remaining groups: the tensors as passed are the consensus variables (raw_inputs)
+      if (dL_dscales && admm.zmu_scale) {
+        const float q0 = scales[3 * idx] - admm.zmu_scale[3 * idx];
+        const float q1 = scales[3 * idx + 1] - admm.zmu_scale[3 * idx + 1];
+        const float q2 = scales[3 * idx + 2] - admm.zmu_scale[3 * idx + 2];
+        g_scale[0] += admm.coef_scale * q0; g_scale[1] += admm.coef_scale * q1; g_scale[2] += admm.coef_scale * q2;
+        pen_scale = (double)(q0 * q0 + q1 * q1 + q2 * q2);
+      }
+      if (dL_drots && admm.zmu_rot) {
+        const float4 xr = reinterpret_cast<const float4*>(rotations)[idx];
+        const float4 zr = reinterpret_cast<const float4*>(admm.zmu_rot)[idx];
+        const float q0 = xr.x - zr.x, q1 = xr.y - zr.y, q2 = xr.z - zr.z, q3 = xr.w - zr.w;
+        g_rot.x += admm.coef_rot * q0; g_rot.y += admm.coef_rot * q1; g_rot.z += admm.coef_rot * q2; g_rot.w += admm.coef_rot * q3;
+        pen_rot = (double)(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+      }
+      if (admm.zmu_opacity) {
+        const float q0 = opacities[idx] - admm.zmu_opacity[idx];
+        g_opacity += admm.coef_opacity * q0;
+        pen_op = (double)(q0 * q0);
+      }
     }
     dL_dmeans3D[3 * idx] = g_mean3D.x; dL_dmeans3D[3 * idx + 1] = g_mean3D.y; dL_dmeans3D[3 * idx + 2] = g_mean3D.z;
     dL_dmeans2D[3 * idx] = g_mean2D.x; dL_dmeans2D[3 * idx + 1] = g_mean2D.y; dL_dmeans2D[3 * idx + 2] = 0.f;
@@ -466,19 +487,48 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       }
     }
   }
-  if (admm.zmu_xyz && admm.sums) {   // penalty sums for logging: one FP64 atomic per warp and group
+  if (pen_partial) {
+    // Penalty sums for logging: one row of 6 partial sums per CTA, folded by penalty_sum_kernel.  (One
+    // FP64 atomic per warp and group on six shared addresses serialised in L2: +0.2 ms per backward.)
+    __shared__ double red[6][PREB_THREADS / 32];
+    double v[6] = {pen_xyz, pen_dc, pen_sh, pen_scale, pen_rot, pen_op};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      pen_xyz += __shfl_xor_sync(0xffffffffu, pen_xyz, o);
-      pen_dc += __shfl_xor_sync(0xffffffffu, pen_dc, o);
-      pen_sh += __shfl_xor_sync(0xffffffffu, pen_sh, o);
+    for (int q = 0; q < 6; q++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+      if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
     }
-    if ((threadIdx.x & 31) == 0) {
-      if (pen_xyz != 0.0) atomicAdd(&admm.sums[0], pen_xyz);
-      if (pen_dc != 0.0) atomicAdd(&admm.sums[1], pen_dc);
-      if (pen_sh != 0.0) atomicAdd(&admm.sums[2], pen_sh);
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < PREB_THREADS / 32; w++) t += red[threadIdx.x][w];
+      pen_partial[(size_t)blockIdx.x * 6 + threadIdx.x] = t;
     }
   }
+}
+
+// sums[g] += sum over CTAs of pen_partial[cta][g]; one CTA per group, fixed order => deterministic.
+__global__ void __launch_bounds__(256)
+penalty_sum_kernel(const double* __restrict__ pen_partial, int nblk, double* __restrict__ sums) {
+  __shared__ double red[8];
+  const int g = blockIdx.x;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) t += pen_partial[(size_t)i * 6 + g];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a += red[w];
+    sums[g] += a;
+  }
+}
+
+size_t bwd_penalty_partial_bytes(size_t P) {
+  return align_up(((P + PREB_THREADS - 1) / PREB_THREADS) * 6 * sizeof(double));
 }
 
 
@@ -488,7 +538,8 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
                           const GeomState& g, const float* accum, float* dL_dmeans3D,
                           float* dL_dmeans2D, float* dL_ddc, float* dL_dsh,
                           float* dL_dcolors_precomp, float* dL_dopacity, float* dL_dscales,
-                          float* dL_drotations, float* dL_dcov3D, cudaStream_t s) {
+                          float* dL_drotations, float* dL_dcov3D, double* pen_partial,
+                          cudaStream_t s) {
   const float focal_y = prm.H / (2.0f * prm.tanfovy);
   const float focal_x = prm.W / (2.0f * prm.tanfovx);
   const bool sh_path = dL_dsh != nullptr && prm.M > 0;
@@ -506,12 +557,18 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
     set_error("preprocess_bwd: SH row too large (M=%d)", prm.M);
     return 1;
   }
-  preprocess_bwd_kernel<<<(prm.P + PREB_THREADS - 1) / PREB_THREADS, PREB_THREADS, smem, s>>>(
+  const int nblk = (prm.P + PREB_THREADS - 1) / PREB_THREADS;
+  const bool sums_on = admm.zmu_xyz != nullptr && admm.sums != nullptr && pen_partial != nullptr;
+  preprocess_bwd_kernel<<<nblk, PREB_THREADS, smem, s>>>(
       prm.P, prm.D, prm.M, means3D, radii, dc, sh, g.clamped, opacities, scales, rotations,
       prm.scale_modifier, cov3D_precomp, prm.viewmatrix, prm.projmatrix, focal_x, focal_y,
       prm.tanfovx, prm.tanfovy, prm.campos, accum, prm.depth_threshold, prm.antialiasing != 0,
       dL_dmeans3D, dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
-      dL_drotations, dL_dcov3D, admm, prm.raw_inputs != 0);
+      dL_drotations, dL_dcov3D, admm, prm.raw_inputs != 0, sums_on ? pen_partial : nullptr);
+  if (sums_on) {
+    penalty_sum_kernel<<<6, 256, 0, s>>>(pen_partial, nblk, admm.sums);
+    return check_launch("preprocess_bwd", prm.debug != 0, s, 2);
+  }
   return check_launch("preprocess_bwd", prm.debug != 0, s);
 }
 

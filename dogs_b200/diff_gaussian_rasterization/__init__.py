@@ -85,6 +85,12 @@ def _params(rs, P, M, device, backward=False):
         pen = L.DgrAdmmPenalty(zmu_xyz=zx.data_ptr(), zmu_dc=zd.data_ptr(), zmu_sh=zs.data_ptr() if M > 0 else None,
                                coef_xyz=coef[0], coef_dc=coef[1], coef_sh=coef[2],
                                sums=blk.fused_sums.data_ptr())
+        if blk.fused_all:    # scaling / quaternion / opacity tensors fed to the rasterizer ARE the consensus variables
+            zc, zq, zo = blk.zmu[3], blk.zmu[4], blk.zmu[5]
+            if zc.numel() != 3 * P or zq.numel() != 4 * P or zo.numel() != P:
+                raise RuntimeError("fused ADMM penalty: the block's tensors do not match the rasterized Gaussians")
+            pen.zmu_scale, pen.zmu_rot, pen.zmu_opacity = zc.data_ptr(), zq.data_ptr(), zo.data_ptr()
+            pen.coef_scale, pen.coef_rot, pen.coef_opacity = coef[3], coef[4], coef[5]
         prm.admm = C.pointer(pen)
         keep = keep + (pen,)
     return prm, keep

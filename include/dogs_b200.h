@@ -34,16 +34,21 @@ typedef char* (*dogs_alloc_fn)(void* user, size_t bytes);
 /* ---- rasterizer ----------------------------------------------------------------
  * Replaces CudaRasterizer::Rasterizer::{forward,backward,visible_filter,markVisible}
  * (cuda_rasterizer/rasterizer.h:22-113) and the glue in rasterize_points.cu:54-252. */
-/* Optional fused ADMM penalty (conerf/trainers/slave_gaussian_trainer.py:161-202) for the three
- * consensus groups that are direct rasterizer inputs (xyz = means3D, f_dc = dc, f_rest = sh): the
- * backward adds coef_g * (x_g - zmu_g) to dL_dmeans3D / dL_ddc / dL_dsh of EVERY Gaussian, with
- * zmu = z - u (admm_unpack_update) and coef_g = rho_g / numel_g, in the pass that writes those
- * gradients anyway.  sums (device double[3], nullable) += sum (x_g - zmu_g)^2 for logging. */
+/* Optional fused ADMM penalty (conerf/trainers/slave_gaussian_trainer.py:161-202) for the consensus
+ * groups that are direct rasterizer inputs: xyz = means3D, f_dc = dc, f_rest = sh always; scaling,
+ * quaternion and opacity when the caller passes the consensus (raw) tensors themselves, i.e. with
+ * DgrParams::raw_inputs.  The backward adds coef_g * (x_g - zmu_g) to the gradient of EVERY Gaussian
+ * for each group whose zmu pointer is set, with zmu = z - u (admm_unpack_update) and
+ * coef_g = rho_g / numel_g, in the pass that writes those gradients anyway.
+ * sums (device double[6] in the order below, nullable) += sum (x_g - zmu_g)^2 for logging. */
 typedef struct DgrAdmmPenalty {
   const float* zmu_xyz;    /* [P,3]   NULL disables the whole fusion */
   const float* zmu_dc;     /* [P,3]   nullable */
   const float* zmu_sh;     /* [P,M,3] nullable */
-  float coef_xyz, coef_dc, coef_sh;
+  const float* zmu_scale;  /* [P,3]   nullable; compared with the `scales` argument as passed */
+  const float* zmu_rot;    /* [P,4]   nullable; compared with `rotations` as passed */
+  const float* zmu_opacity;/* [P]     nullable; compared with `opacities` as passed */
+  float coef_xyz, coef_dc, coef_sh, coef_scale, coef_rot, coef_opacity;
   double* sums;
 } DgrAdmmPenalty;
 

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16
     assert _lib.DgrParams.bg.offset == 48 and _lib.DgrParams.ref_bucket_cull_quirk.offset == 80
     assert _lib.DgrParams.raw_inputs.offset == 84 and _lib.DgrParams.admm.offset == 88
-    assert C.sizeof(_lib.DgrAdmmPenalty) == 3 * 8 + 3 * 4 + 4 + 8
+    assert C.sizeof(_lib.DgrAdmmPenalty) == 6 * 8 + 6 * 4 + 8
     assert C.sizeof(_lib.DgrLayout) == 11 * 8
     assert C.sizeof(_lib.AdmmTensors) == 48
 

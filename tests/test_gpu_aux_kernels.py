@@ -203,7 +203,7 @@ def test_fused_admm_penalty_in_rasterizer_backward_matches_standalone():
             v.requires_grad_(True)
         return d
 
-    def run(fused):
+    def run(fused, all_groups=False):
         lv = leaves()
         plan = A.ConsensusPlan(torch.arange(P, device=DEV), torch.full((P,), 2, dtype=torch.int32, device=DEV))
         x = [lv[k] for k in ("means3D", "dc", "sh", "scales", "rotations", "opacities")]
@@ -211,7 +211,7 @@ def test_fused_admm_penalty_in_rasterizer_backward_matches_standalone():
         gg = torch.Generator(device="cpu").manual_seed(5)
         for t in blk.zmu:                                   # pretend a consensus round happened
             t.add_(0.05 * torch.randn(t.shape, generator=gg).to(DEV))
-        blk.fuse_into_rasterizer(fused)
+        blk.fuse_into_rasterizer(fused, all_groups=all_groups)
         try:
             views = dict(lv)
             views["dc"] = lv["dc"].view(P, 1, 3)
@@ -225,10 +225,11 @@ def test_fused_admm_penalty_in_rasterizer_backward_matches_standalone():
         return {k: v.grad.clone() for k, v in lv.items()}, pens.clone()
 
     g0, p0 = run(False)
-    g1, p1 = run(True)
-    assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-15)
-    for k in g0:
-        assert U.rel_to_max(g1[k], g0[k]) <= 2e-6, k
+    for all_groups in (False, True):   # True: scaling / quaternion / opacity fused as well (no penalty kernel at all)
+        g1, p1 = run(True, all_groups)
+        assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-15)
+        for k in g0:
+            assert U.rel_to_max(g1[k], g0[k]) <= 2e-6, (k, all_groups)
 
 
 def test_importance_count_render_vs_oracle():
