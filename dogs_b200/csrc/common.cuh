@@ -132,8 +132,14 @@ __device__ __forceinline__ float4 act_normalize(float4 q) {
 // Per-tile reachability test of the key-duplication stage
 // (rasterizer_impl.cu:52-100 max_contrib_power_rect_gaussian_float<15,15> + :151-173).
 // Returns true iff the Gaussian can reach alpha >= 1/255 somewhere in tile (tx,ty).
+// The two reciprocals depend on the Gaussian only; callers that walk a whole rect compute them once
+// (tile_rcps) — same operations on the same operands, so the decisions are unchanged.
+__device__ __forceinline__ float2 tile_rcps(const float4 co) {
+  return {__frcp_rn((uint32_t)((TILE_X - 1) * (TILE_X - 1)) * co.x),
+          __frcp_rn((uint32_t)((TILE_Y - 1) * (TILE_Y - 1)) * co.z)};
+}
 __device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mean, int tx, int ty,
-                                               float thr) {
+                                               float thr, const float2 rcps) {
   const float rminx = (float)(tx * TILE_X), rminy = (float)(ty * TILE_Y);
   const float rmaxx = (float)((tx + 1) * TILE_X - 1), rmaxy = (float)((ty + 1) * TILE_Y - 1);
   const float x_min_diff = rminx - mean.x;
@@ -150,8 +156,8 @@ __device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mea
     const float dy = copysignf(float(TILE_Y - 1), y_min_diff);
     const float diffx = mean.x - px;
     const float diffy = mean.y - py;
-    const float rcp_dxdxcox = __frcp_rn((uint32_t)((TILE_X - 1) * (TILE_X - 1)) * co.x);
-    const float rcp_dydycoz = __frcp_rn((uint32_t)((TILE_Y - 1) * (TILE_Y - 1)) * co.z);
+    const float rcp_dxdxcox = rcps.x;
+    const float rcp_dydycoz = rcps.y;
     const float tx_ = not_in_y_range * __saturatef((dx * co.x * diffx + dx * co.y * diffy) * rcp_dxdxcox);
     const float ty_ = not_in_x_range * __saturatef((dy * co.y * diffx + dy * co.z * diffy) * rcp_dydycoz);
     const float mx = px + tx_ * dx, my = py + ty_ * dy;
@@ -159,6 +165,10 @@ __device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mea
     max_contrib_power = 0.5f * (co.x * ddx * ddx + co.z * ddy * ddy) + co.y * ddx * ddy;
   }
   return max_contrib_power <= thr;
+}
+__device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mean, int tx, int ty,
+                                               float thr) {
+  return tile_reachable(co, mean, tx, ty, thr, tile_rcps(co));
 }
 
 // Internal per-Gaussian record written by preprocess and gathered by the blend kernels.

@@ -217,9 +217,10 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       big_co = co; big_xy = point_image; big_thr = thr;
       big_x0 = rect_min.x; big_y0 = rect_min.y; big_w = rw; big_n = ntot;
     } else {
+      const float2 rcps = tile_rcps(co);
       for (int y = rect_min.y; y < (int)rect_max.y; y++)
         for (int x = rect_min.x; x < (int)rect_max.x; x++)
-          if (tile_reachable(co, point_image, x, y, thr)) {
+          if (tile_reachable(co, point_image, x, y, thr, rcps)) {
             ntiles++;
             mask |= 1ull << ((y - (int)rect_min.y) * rw + (x - (int)rect_min.x));
           }
@@ -243,12 +244,13 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       const int x0 = __shfl_sync(full, big_x0, src), y0 = __shfl_sync(full, big_y0, src);
       const int w = __shfl_sync(full, big_w, src), n = __shfl_sync(full, big_n, src);
       uint32_t cnt = 0, mlo = 0, mhi = 0;
+      const float2 rcps = tile_rcps(co);
       for (int base = 0; base < n; base += 32) {
         const int t = base + lane;
         bool r = false;
         if (t < n) {
           const int ty = t / w, tx = t - ty * w;
-          r = tile_reachable(co, xy, x0 + tx, y0 + ty, thr);
+          r = tile_reachable(co, xy, x0 + tx, y0 + ty, thr, rcps);
         }
         const unsigned b = __ballot_sync(full, r);
         cnt += __popc(b);
@@ -361,6 +363,7 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
     const float4 co = rec[idx].a;
     const float thr = logf(co.w / (1.0f / 255.0f));
     const int w = rect_max.x - rect_min.x, n = w * (int)(rect_max.y - rect_min.y);
+    const float2 rcps = tile_rcps(co);
     for (int base = 0; base < n; base += 32) {
       const int t = base + lane;
       bool r = false;
@@ -369,7 +372,7 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
         const int ty = t / w;
         x = rect_min.x + (t - ty * w);
         y = rect_min.y + ty;
-        r = tile_reachable(co, xy, x, y, thr);
+        r = tile_reachable(co, xy, x, y, thr, rcps);
       }
       const unsigned bal = __ballot_sync(full, r);
       if (r) {
