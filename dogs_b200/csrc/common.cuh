@@ -175,6 +175,17 @@ __device__ __forceinline__ bool tile_reachable(const float4 co, const float2 mea
 // a = {conic.x, conic.y, conic.z, opacity}, b = {x, y, 1/depth, r}, c = {g, b, depth, ln(255*opacity)}
 struct __align__(16) SplatRecord { float4 a, b, c; };
 
+// The opt-in dynamic shared-memory limit is a per-device function attribute: set it once per device
+// the library is used on (a process may drive several GPUs).
+template <typename K> static void allow_big_smem(K kernel, bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+}
+
 // ---- stage launchers (defined in the .cu files) -----------------------------------
 struct GeomState {
   SplatRecord* rec; uint8_t* clamped; uint32_t* tiles; uint32_t* depth_key;

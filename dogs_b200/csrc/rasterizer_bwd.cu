@@ -548,11 +548,8 @@ int launch_preprocess_bwd(const DgrParams& prm, const float* means3D, const floa
   if (prm.admm) admm = *prm.admm;
   if (!sh_path) admm.zmu_sh = nullptr;
   size_t smem = sh_path ? (size_t)PREB_THREADS * 3 * prm.M * sizeof(float) + 16 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  allow_big_smem(preprocess_bwd_kernel, attr_set);
   if (smem > 96 * 1024) {
     set_error("preprocess_bwd: SH row too large (M=%d)", prm.M);
     return 1;

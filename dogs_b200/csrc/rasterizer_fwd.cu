@@ -475,11 +475,8 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   const bool use_sh = colors_precomp == nullptr && prm.D > 0 && prm.M > 0;
   size_t smem = use_sh ? (size_t)PRE_THREADS * 3 * prm.M * sizeof(float) + 16 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};
+  allow_big_smem(preprocess_fwd_kernel, attr_set);
   if (smem > 96 * 1024) {
     set_error("preprocess: SH row too large (M=%d)", prm.M);
     return 1;

@@ -116,3 +116,42 @@ def test_apply_activations_bit_exact_vs_torch():
     assert torch.equal(U.bits(o), U.bits(torch.sigmoid(op)))
     assert torch.equal(U.bits(s), U.bits(torch.exp(sc)))
     assert torch.equal(U.bits(r), U.bits(torch.nn.functional.normalize(rot)))
+
+
+def test_raw_activations_with_all_group_admm_fusion():
+    """The full fused iteration: raw parameters in, activations + all six ADMM penalty groups inside the
+    rasterizer backward, against torch activations + rasterizer + stand-alone admm_penalty."""
+    from dogs_b200 import admm as A
+    raw = _raw_scene("tiny", 3)
+    P = raw["means3D"].shape[0]
+    g = torch.Generator(device="cpu").manual_seed(9)
+    w = torch.randn(3, raw["H"], raw["W"], generator=g).to(DEV)
+    order = ("means3D", "dc", "sh", "scales", "rotations", "opacities")
+
+    def run(fused):
+        lv = {"means3D": raw["means3D"].clone(), "dc": raw["dc"].reshape(P, 3).clone(),
+              "sh": raw["sh"].reshape(P, 45).clone(), "scales": raw["scales"].clone(),
+              "rotations": raw["rotations"].clone(), "opacities": raw["opacities"].clone()}
+        for v in lv.values():
+            v.requires_grad_(True)
+        plan = A.ConsensusPlan(torch.arange(P, device=DEV), torch.full((P,), 2, dtype=torch.int32, device=DEV))
+        blk = A.AdmmBlock([lv[k] for k in order], plan, alphas=(3e3, 2e3, 5e3, 1e3, 7e3, 9e2))
+        gg = torch.Generator(device="cpu").manual_seed(5)
+        for t in blk.zmu:
+            t.add_(0.05 * torch.randn(t.shape, generator=gg).to(DEV))
+        blk.fuse_into_rasterizer(fused, all_groups=fused)
+        try:
+            leaves = dict(lv, dc=lv["dc"].view(P, 1, 3), sh=lv["sh"].view(P, 15, 3))
+            img = _render(raw, fused, False, leaves)[0]
+            (img * w).sum().backward()
+            pens = blk.add_penalty_grads_().clone()
+        finally:
+            blk.fuse_into_rasterizer(False)
+        torch.cuda.synchronize()
+        return {k: v.grad.clone() for k, v in lv.items()}, pens
+
+    g0, p0 = run(False)
+    g1, p1 = run(True)
+    assert torch.allclose(p0, p1, rtol=1e-6, atol=1e-15)
+    for k in order:
+        assert U.rel_to_max(g1[k], g0[k]) <= GRAD_TOL, k
