@@ -276,6 +276,43 @@ def test_ragged_image_and_nonzero_background_vs_reference():
         assert U.rel_to_max(p[k].grad, gr[k].reshape(p[k].grad.shape)) <= GRAD_TOL, k
 
 
+@pytest.mark.parametrize("P", [1, 31, 77, 1000])
+def test_mixed_rect_sizes_vs_reference(P):
+    """Every branch of the rect walk in preprocess / emit: Gaussians whose rect has <= 16 tiles (walked
+    by their own thread), 17-64 tiles (walked by the warp, bit mask recorded) and > 64 tiles up to the
+    whole image (walked by the warp again at emission), in warps that are only partly populated."""
+    dgr = _need_ref()
+    spec = scenes.SPECS["tiny"]._replace(W=400, H=304)
+    sc = scenes.make_scene(spec, 21, DEV, P=P)
+    g = torch.Generator(device="cpu").manual_seed(22)
+    # log-uniform scale multiplier 1x .. 150x: footprints from a couple of pixels to the full frame
+    mult = torch.exp(torch.rand(P, 1, generator=g) * 5.0).to(DEV)
+    sc["scales"] = (sc["scales"] * mult).contiguous()
+    r = U.ref_forward_raw(dgr, sc)
+    o = U.ours_forward_raw(sc)
+    H, W = sc["H"], sc["W"]
+    tiles = o["tiles"].long()
+    if P >= 77:
+        assert int((tiles > 64).sum()) > 0 and int(((tiles > 16) & (tiles <= 64)).sum()) > 0 and int((tiles <= 16).sum()) > 0
+    ri = U.parse_ref_image(r["img"], H * W)
+    assert torch.equal(r["radii"], o["radii"])
+    rb = U.parse_ref_binning(r["binning"], r["num_rendered"])
+    valid = ((rb["keys"] >> 32) & 0xFFFFFFFF) != 0xFFFFFFFF
+    keys = (o["tile_keys"].long() << 32) | (U.bits(o["depths"]).long()[o["point_list"].long()] & 0xFFFFFFFF)
+    assert torch.equal(rb["keys"][valid], keys)
+    assert torch.equal(rb["point_list"][valid].long(), o["point_list"].long())
+    assert torch.equal(ri["n_contrib"], o["n_contrib"])
+    assert torch.equal(U.bits(ri["accum_alpha"]), U.bits(o["final_T"]))
+    assert (r["color"] - o["color"]).abs().max().item() <= IMG_TOL
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
+    dLc, dLd = _out_grads(sc)
+    gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+    go = U.ours_backward(sc, dLc, dLd)
+    for k in GRAD_KEYS:
+        assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, k
+
+
 @pytest.mark.parametrize("cfg", ["C3"])
 def test_full_size_properties(cfg):
     """BASELINE.json's headline size: exact forward parity with the reference plus
