@@ -77,6 +77,7 @@ SIGNATURES = {
     "fssim_l1_loss_forward": [C.c_int32] * 4 + [C.c_float] * 3 + [_P] * 5 + [_P, _P, _P],
     "fssim_l1_loss_backward": [C.c_int32] * 4 + [C.c_float] * 2 + [_P] * 5 + [_P, _P, _P],
     "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],
+    "admm_block_membership": [C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P],
     "admm_pack": [C.POINTER(AdmmTensors), _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "admm_unpack_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, _P, C.c_int64, _P, C.c_float, _P, _P],
     "admm_penalty": [C.POINTER(AdmmTensors)] * 3 + [_P, C.c_int64, _P, _P, _P],

@@ -240,3 +240,59 @@ class AdmmBlock:
         not persist z / indices)."""
         return dict(u=self.u, z=self.z, rho=list(self.rho), slot_of_local=self.plan.slot_of_local,
                     inv_count=self.plan.inv_count)
+
+
+# ---- fusion / re-split of the blocks (once per run, before ADMM starts) ----------------------------
+def _boxes2d(bboxes, device):
+    """[n_blocks, 2, 3] (or [n_blocks, 6]) min/max corners as the reference stores them -> [n_blocks, 4]
+    float64 {min_x, min_y, max_x, max_y} (points_in_bbox2D only looks at x and y)."""
+    b = torch.as_tensor(bboxes, dtype=torch.float64).reshape(-1, 2, 3)
+    return torch.cat([b[:, 0, :2], b[:, 1, :2]], dim=1).contiguous().to(device)
+
+
+def block_membership(xyz: torch.Tensor, bboxes, world_to_obb=None):
+    """(mask int64 [N], count int32 [N]): bit b of mask[i] = Gaussian i lies in block b's box
+    (points_in_bbox2D, conerf/datasets/utils.py:186-205, for all blocks in one pass on the GPU)."""
+    from . import _lib as L
+    xyz = L.require_cuda(xyz.detach(), "xyz")
+    n = xyz.shape[0]
+    boxes = _boxes2d(bboxes, xyz.device)
+    mask = torch.zeros(n, dtype=torch.int64, device=xyz.device)
+    count = torch.zeros(n, dtype=torch.int32, device=xyz.device)
+    t = None
+    if world_to_obb is not None:
+        t = (C.c_double * 9)(*[float(v) for v in torch.as_tensor(world_to_obb, dtype=torch.float64).reshape(-1)])
+    with torch.cuda.device(xyz.device):
+        L.check(L.lib().admm_block_membership(n, xyz.data_ptr(), t, boxes.shape[0], boxes.data_ptr(),
+                                              mask.data_ptr(), count.data_ptr(), L.stream_ptr(xyz.device)))
+    return mask, count
+
+
+def select_gaussians_in_each_block(xyz: torch.Tensor, bboxes, world_to_obb=None):
+    """GPU restatement of master_gaussian_trainer.select_gaussians_in_each_block (:124-172).
+    Returns (valid_gaussian_indices, visibility_count, global_indices):
+      valid_gaussian_indices  int64 [N'] Gaussians inside at least one box (feed to extract_sub_gaussians),
+      visibility_count        int64 [N'] number of blocks holding each kept Gaussian (the bincount),
+      global_indices          list over blocks of int64 index tensors into the kept Gaussians, ascending."""
+    mask, count = block_membership(xyz, bboxes, world_to_obb)
+    valid = torch.nonzero(count).squeeze(-1)
+    mask, count = mask[valid], count[valid]
+    n_blocks = _boxes2d(bboxes, "cpu").shape[0]
+    global_indices = [torch.nonzero((mask >> b) & 1).squeeze(-1) for b in range(n_blocks)]
+    return valid, count.to(torch.int64), global_indices
+
+
+def fuse_block_gaussians(block_params: Sequence[Sequence[torch.Tensor]], point_bboxes=None, world_to_obb=None):
+    """GPU restatement of master_gaussian_trainer.fuse_block_gaussians (:37-105) without its .ply dumps:
+    every block first drops the Gaussians outside its own initial box, then the six parameter tensors
+    (xyz, f_dc, f_rest, raw scaling, raw quaternion, raw opacity) are concatenated block by block."""
+    kept = []
+    for b, params in enumerate(block_params):
+        params = list(params)
+        if point_bboxes is not None:
+            box = torch.as_tensor(point_bboxes[b], dtype=torch.float64).reshape(1, 2, 3)
+            mask, _ = block_membership(params[0], box, world_to_obb)
+            idx = torch.nonzero(mask).squeeze(-1)
+            params = [t.detach()[idx] for t in params]
+        kept.append(params)
+    return [torch.cat([k[g] for k in kept], dim=0) for g in range(6)]

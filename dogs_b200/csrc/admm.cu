@@ -216,3 +216,51 @@ extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u
   admm_penalty_kernel<<<grid_for(end), ADMM_THREADS, 0, s>>>(a, sums);
   return check_launch("admm_penalty", false, s);
 }
+
+// ---- block membership (re-split after fusion) ------------------------------------------------------
+// select_gaussians_in_each_block / fuse_block_gaussians (master_gaussian_trainer.py:37-172) test every
+// Gaussian against every block's 2-D bounding box on the host (numpy, one argwhere per block, after
+// trimesh.transform_points with the world->OBB matrix).  One pass here: bit b of mask[i] = Gaussian i
+// lies inside box b (closed interval, as conerf/datasets/utils.py:186-205), count[i] = popcount.
+// The transform and the comparisons run in FP64 like numpy's (float32 points promoted to double).
+namespace dogs {
+struct BoxSet { double t[9]; int has_t; int n; };
+__global__ void __launch_bounds__(256)
+block_membership_kernel(int64_t n, const float* __restrict__ xyz, const BoxSet bs,
+                        const double* __restrict__ boxes, unsigned long long* __restrict__ mask,
+                        int32_t* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = (double)xyz[3 * i], y = (double)xyz[3 * i + 1];
+  if (bs.has_t) {   // trimesh.transform_points on 2-D points: (M . [x, y, 1]^T)[:2], no perspective divide
+    const double ox = bs.t[0] * x + bs.t[1] * y + bs.t[2];
+    const double oy = bs.t[3] * x + bs.t[4] * y + bs.t[5];
+    x = ox; y = oy;
+  }
+  unsigned long long m = 0ull;
+  for (int b = 0; b < bs.n; b++) {
+    const double ax = boxes[4 * b], ay = boxes[4 * b + 1], bx = boxes[4 * b + 2], by = boxes[4 * b + 3];
+    if (ax <= x && x <= bx && ay <= y && y <= by) m |= 1ull << b;
+  }
+  mask[i] = m;
+  if (count) count[i] = __popcll(m);
+}
+}  // namespace dogs
+
+extern "C" int admm_block_membership(int64_t n, const float* xyz, const double* world_to_obb,
+                                     int32_t n_blocks, const double* boxes, uint64_t* mask,
+                                     int32_t* count, void* stream) {
+  using namespace dogs;
+  if (n < 0 || n_blocks < 1 || n_blocks > 64) { set_error("admm_block_membership: 1..64 blocks supported"); return 1; }
+  if (n == 0) return 0;
+  if (!xyz || !boxes || !mask) { set_error("admm_block_membership: null pointer"); return 1; }
+  BoxSet bs;
+  bs.has_t = world_to_obb != nullptr;
+  bs.n = n_blocks;
+  for (int k = 0; k < 9; k++) bs.t[k] = world_to_obb ? world_to_obb[k] : 0.0;
+  cudaStream_t s = (cudaStream_t)stream;
+  block_membership_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      n, xyz, bs, boxes, reinterpret_cast<unsigned long long*>(mask), count);
+  return check_launch("admm_block_membership", false, s);
+}
+

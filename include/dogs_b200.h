@@ -247,6 +247,16 @@ int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u, const Adm
                  const AdmmTensors* grad, int64_t n, const float* coef /* host[6] */,
                  double* sums /* device[6] */, void* stream);
 
+/* Block membership for the re-split after fusion (select_gaussians_in_each_block /
+ * fuse_block_gaussians, conerf/trainers/master_gaussian_trainer.py:37-172, points_in_bbox2D
+ * conerf/datasets/utils.py:186-205): bit b of mask[i] = Gaussian i is inside block b's closed 2-D box
+ * boxes[b] = {min_x, min_y, max_x, max_y} (device double[n_blocks*4]) after the optional world->OBB
+ * transform (host double[9], row-major 3x3 as passed to trimesh.transform_points; NULL = identity);
+ * count[i] (nullable) = number of blocks holding i = torch.bincount of the reference.  <= 64 blocks. */
+int admm_block_membership(int64_t n, const float* xyz, const double* world_to_obb,
+                          int32_t n_blocks, const double* boxes, uint64_t* mask, int32_t* count,
+                          void* stream);
+
 const char* dogs_last_error(void);
 int dogs_abi_version(void);
 /* Number of kernels this library has launched so far in the process (bench.py reports the delta). */

@@ -247,3 +247,32 @@ def admm_adapt(rho, primal, dual, mu=10.0, tau_inc=2.0, tau_dec=2.0):
         elif dual[g] > mu * primal[g]:
             out[g] /= tau_dec
     return out
+
+
+def points_in_bbox2d(points, bbox, transform_world_to_obb=None):
+    """conerf/datasets/utils.py:186-205.  points [N,2] (float32, as model.get_xyz.cpu().numpy()[:, :2]),
+    bbox [2,3] min/max corners; trimesh.transform_points on 2-D points = (M . [x, y, 1]^T)[:2] in
+    float64, no perspective divide."""
+    A, B = bbox[0, :], bbox[1, :]
+    pts = points
+    if transform_world_to_obb is not None:
+        M = np.asarray(transform_world_to_obb, np.float64)
+        stack = np.column_stack((points, np.ones(len(points))))
+        pts = np.dot(M, stack.T).T[:, :2]
+    return np.argwhere((A[0] <= pts[:, 0]) & (pts[:, 0] <= B[0]) & (A[1] <= pts[:, 1]) & (pts[:, 1] <= B[1])).reshape(-1)
+
+
+def select_gaussians_in_each_block(xyz, bboxes, transform_world_to_obb=None):
+    """master_gaussian_trainer.py:124-172: drop Gaussians that lie in no box, regroup the rest per box.
+    Returns (valid_gaussian_indices, visibility_count, global_indices)."""
+    pts = np.asarray(xyz, np.float32)[:, :2]
+    first = [points_in_bbox2d(pts, np.asarray(b, np.float64).reshape(2, 3), transform_world_to_obb) for b in bboxes]
+    visibility = np.bincount(np.concatenate(first), minlength=len(pts))
+    valid = np.argwhere(visibility).reshape(-1)
+    pts = pts[valid]
+    global_indices = [points_in_bbox2d(pts, np.asarray(b, np.float64).reshape(2, 3), transform_world_to_obb)
+                      for b in bboxes]
+    visibility = np.bincount(np.concatenate(global_indices), minlength=len(pts))
+    assert (visibility != 0).all()
+    return valid, visibility, global_indices
+

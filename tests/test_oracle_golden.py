@@ -116,3 +116,18 @@ def test_adam_golden():
     assert np.array_equal(bits(p), bits(g["param_out"]))
     untouched = ~g["visible"]
     assert np.array_equal(p[untouched], g["param"][untouched])
+
+
+def test_block_split_oracle_matches_hand_example():
+    """select_gaussians_in_each_block (master:124-172) on a case small enough to check by hand."""
+    from oracle import oracle as O
+    xyz = np.array([[0.5, 0.5, 0], [1.5, 0.5, 0], [2.5, 0.5, 0], [9.0, 9.0, 0], [1.0, 1.0, 0]], np.float32)
+    boxes = np.array([[[0, 0, -1], [1.6, 1, 1]], [[1.4, 0, -1], [3, 1, 1]]], np.float64)   # overlap 1.4..1.6
+    valid, vis, gidx = O.select_gaussians_in_each_block(xyz, boxes)
+    assert valid.tolist() == [0, 1, 2, 4]              # (9, 9) lies in no box
+    assert vis.tolist() == [1, 2, 1, 1]                # x = 1.5 is shared; the closed box includes (1, 1)
+    assert [g.tolist() for g in gidx] == [[0, 1, 3], [1, 2]]
+    # world -> OBB transform: a shift by (-1, 0) moves everything one box to the left
+    M = np.array([[1, 0, -1.0], [0, 1, 0], [0, 0, 1]], np.float64)
+    valid, vis, gidx = O.select_gaussians_in_each_block(xyz, boxes, M)
+    assert valid.tolist() == [1, 2, 4] and [g.tolist() for g in gidx] == [[0, 1, 2], [1]]
