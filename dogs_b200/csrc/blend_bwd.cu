@@ -161,6 +161,16 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
   const int rounds = (todo_total + BB_BATCH - 1) / BB_BATCH;
   const int my_slot = bb_slot(lane);
+  // blast[k] = last list position any pixel of the warp's k-th 8x4 block still blends (after the quirk
+  // cut): entries at or beyond it are dead for the whole block and are dropped with the geometric cull
+  uint32_t blast[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t v = last[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    blast[k] = v;
+  }
 
   auto fetch = [&](int round, int buf) {
     uint32_t progress = round * BB_BATCH + tid;
@@ -197,7 +207,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float thr = sC[buf][jj].w;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          m4 |= (uint32_t)block_reachable(aa, bb.x, bb.y, rx0, ry0 + 4.f * k, rx0 + 7.f, ry0 + 4.f * k + 3.f, thr) << k;
+          m4 |= (uint32_t)(base + jj < blast[k] &&
+                           block_reachable(aa, bb.x, bb.y, rx0, ry0 + 4.f * k, rx0 + 7.f, ry0 + 4.f * k + 3.f, thr)) << k;
       }
       bm[w] = m4;
       hm[w] = __ballot_sync(0xffffffffu, m4 != 0);
