@@ -90,7 +90,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ float4 sB[2][BB_BATCH];
   __shared__ float4 sC[2][BB_BATCH];
   __shared__ uint32_t sId[2][BB_BATCH];
-  __shared__ float sAcc[BB_BATCH][11];
+  // Per-warp totals of the batch: a warp meets an entry at most once per round, so it simply STORES its
+  // 10 totals (no shared-memory float atomic, which is a compare-and-swap loop on this hardware); sWritten
+  // says which entries each warp wrote, the flush adds the two halves.
+  __shared__ float sAcc[2][BB_BATCH][11];
+  __shared__ uint32_t sWritten[2][2];
   __shared__ uint32_t sMax, sMaxRows01;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,8 +141,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const float ddely_dy = 0.5 * H;
 
   if (tid == 0) { sMax = 0; sMaxRows01 = 0; }
-#pragma unroll
-  for (int k = 0; k < 11; k++) sAcc[tid][k] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -217,6 +219,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #pragma unroll
     for (int w = 0; w < 2; w++) {
     uint32_t m = hm[w];
+    uint32_t wrote = 0;
     while (m) {
       const int bit = __ffs(m) - 1;
       m &= m - 1;
@@ -277,21 +280,19 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       }
       if (!any_c) continue;
       const float tot = bb_warp_reduce10(v, lane);
-      if (my_slot >= 0) atomicAdd(&sAcc[j][my_slot], tot);
+      if (my_slot >= 0) sAcc[warp][j][my_slot] = tot;
+      wrote |= 1u << bit;
     }
+    if (lane == 0) sWritten[warp][w] = wrote;
     }
     __syncthreads();
     // flush the batch: thread t owns splat t
     if (tid < nbatch) {
       float a[10];
-      bool nz = false;
+      const bool w0 = (sWritten[0][tid >> 5] >> (tid & 31)) & 1u, w1 = (sWritten[1][tid >> 5] >> (tid & 31)) & 1u;
 #pragma unroll
-      for (int q = 0; q < 10; q++) {
-        a[q] = sAcc[tid][q];
-        nz |= (a[q] != 0.f);
-        sAcc[tid][q] = 0.f;
-      }
-      if (nz) {
+      for (int q = 0; q < 10; q++) a[q] = (w0 ? sAcc[0][tid][q] : 0.f) + (w1 ? sAcc[1][tid][q] : 0.f);
+      if (w0 | w1) {
         // moments -> gradients (backward.cu:626-641):  dL/dG * G = o * q
         const float4 co = sA[buf][tid];
         const float o = co.w;
