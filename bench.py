@@ -242,6 +242,21 @@ def main():
             plan = A.build_plan(gidx.to(dev), n_global).to(dev)
         x = [leaves[k] for k in ("means3D", "dc", "sh", "scales", "rotations", "opacities")]
         admm = A.AdmmBlock(x, plan)                  # penalty gradients accumulate into the leaves' .grad
+        admm_check = None
+        if distributed:
+            # untimed self-check of the exchange: one consensus round through the point-to-point neighbour
+            # exchange must give the same z as the dense all-reduce over all shared Gaussians
+            ref_blk = A.AdmmBlock([t.detach().clone() for t in x],
+                                  A.build_plan(gidx.to(dev), n_global, exchange="dense").to(dev))
+            chk_blk = A.AdmmBlock([t.detach().clone() for t in x], plan)
+            ref_blk.consensus(adapt=False)
+            chk_blk.consensus(adapt=False)
+            dz = torch.stack([(a - b).abs().max() for a, b in zip(ref_blk.z, chk_blk.z)]).max()
+            dist.all_reduce(dz, op=dist.ReduceOp.MAX)
+            admm_check = {"neighbour_vs_dense_max_abs_dz": float(dz.item()),
+                          "peers": [int(r) for r, _ in (plan.peers or [])]}
+            del ref_blk, chk_blk
+            torch.cuda.empty_cache()
         # the six leaf tensors fed to the rasterizer are the consensus variables themselves, so the whole
         # penalty (all 59 floats per Gaussian) is added by the rasterizer backward
         admm.fuse_into_rasterizer(True, all_groups=True)
@@ -400,6 +415,7 @@ def main():
                                 else "torch L1 ops + fused_ssim"),
                        "blocks": world if args.impl == "ours" else 1},
             "gpu_launches": int(launches), "clocks": clk.summary(),
+            **({"admm_check": admm_check} if admm is not None and admm_check is not None else {}),
             "step_ms": {"min": per_step[0], "median": per_step[K // 2], "max": per_step[-1]},
         }
         if args.impl == "reference":

@@ -8,6 +8,8 @@ Replaces the master/slave RPC round of the reference
   send_local_model: every block ships all 59 floats/G      pack: only Gaussians owned by >= 2 blocks are
   to GPU0; z = scatter-add / count (master:538-555)        gathered into a dense [S_total,59] buffer
   broadcast_global_gaussian_splat (master:523-535)         ONE all-reduce(sum) over NVLink on that buffer
+                                                           (default: neighbour exchange - each rank sends its shared
+                                                           rows only to the other owners, traffic independent of N)
   update_dual_variables (slave:99-121)                     unpack_update kernel: z = sum/count, u += 1.5(x-z),
   compute_primal/dual_residual (master:396-456)            partial residual sums in the same pass
   adapt_penalty_parameters + set_penalty (master:337-393)  12-double all-reduce, identical rho update on every rank
@@ -50,20 +52,74 @@ class ConsensusPlan:
         self.local_idx = torch.nonzero(is_shared).squeeze(1).contiguous()
         self.slot = self.slot_of_local[self.local_idx].contiguous()
         self.S = int(self.local_idx.numel())
+        # neighbour exchange: position of each local Gaussian in this rank's OWN compact buffer [S, 59]
+        # and, per peer rank that co-owns Gaussians, the rows of that buffer exchanged with it (ordered by
+        # global index, so both sides agree); filled by build_plan(exchange="neighbour")
+        self.compact_slot_of_local = torch.where(
+            is_shared, torch.cumsum(is_shared.to(torch.int64), 0) - 1, torch.full_like(global_indices, -1)).contiguous()
+        self.peers = None
 
     def to(self, device):
-        for k in ("slot_of_local", "inv_count", "local_idx", "slot"):
+        for k in ("slot_of_local", "inv_count", "local_idx", "slot", "compact_slot_of_local"):
             setattr(self, k, getattr(self, k).to(device))
+        if self.peers is not None:
+            self.peers = [(r, rows.to(device)) for r, rows in self.peers]
         return self
 
+    def compact(self):
+        """The same plan addressed through the rank-local buffer (slot = 0..S-1) instead of the global
+        dense one: what pack / unpack_update see in neighbour-exchange mode."""
+        import copy
+        p = copy.copy(self)
+        p.slot_of_local = self.compact_slot_of_local
+        p.slot = torch.arange(self.S, dtype=torch.int64, device=self.local_idx.device)
+        p.S_total = self.S
+        return p
 
-def build_plan(global_indices: torch.Tensor, n_global: int, group=None) -> ConsensusPlan:
+
+def build_plan(global_indices: torch.Tensor, n_global: int, group=None, exchange: str = "neighbour") -> ConsensusPlan:
     """count[i] = number of blocks holding global Gaussian i (torch.bincount at master:168),
-    obtained with one all-reduce instead of on a master."""
+    obtained with one all-reduce instead of on a master.
+    exchange="neighbour" (default) also finds, once, which rows are co-owned with which rank, so that a
+    consensus round sends every shared row only to its other owners (point-to-point, S_k * 236 B per rank
+    whatever the number of blocks); exchange="dense" keeps the single all-reduce over the [S_total, 59]
+    buffer of ALL shared Gaussians, which grows with the number of blocks (1.2 GB at 8 x 3 M)."""
     count = torch.bincount(global_indices, minlength=n_global).to(torch.int32)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
         dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
-    return ConsensusPlan(global_indices, count)
+    plan = ConsensusPlan(global_indices, count)
+    if multi and exchange == "neighbour":
+        plan.peers = _find_peers(global_indices, n_global, plan, group)
+    return plan
+
+
+def _find_peers(global_indices, n_global, plan, group):
+    """[(peer rank in group, rows of the local compact buffer co-owned with it, ordered by global index)]"""
+    dev = global_indices.device
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = torch.tensor([global_indices.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    pad = torch.full((max(max(sizes), 1),), -1, dtype=torch.int64, device=dev)
+    pad[:global_indices.numel()] = global_indices
+    gathered = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad, group=group)
+    peers = []
+    mark = torch.zeros(n_global, dtype=torch.bool, device=dev)
+    for r in range(world):
+        if r == rank or sizes[r] == 0:
+            continue
+        theirs = gathered[r][:sizes[r]]
+        mark.zero_()
+        mark[theirs] = True
+        rows_local = torch.nonzero(mark[global_indices]).squeeze(1)
+        if rows_local.numel() == 0:
+            continue
+        rows_local = rows_local[torch.argsort(global_indices[rows_local])]
+        peers.append((r, plan.compact_slot_of_local[rows_local].contiguous()))
+    return peers
 
 
 class CudaOps:
@@ -143,7 +199,12 @@ class AdmmBlock:
         self.rho = [a / plan.n_global for a in alphas]
         self.relax = 1.0 + over_relaxation_coeff
         self.mu, self.tau_inc, self.tau_dec = mu, tau_inc, tau_dec
-        self.buf = torch.zeros(max(plan.S_total, 1) * ROW, dtype=torch.float32, device=dev)
+        # exchange buffer: the rank's own shared rows (neighbour exchange) or all shared rows (dense all-reduce)
+        self.neighbour = plan.peers is not None
+        self.xplan = plan.compact() if self.neighbour else plan
+        self.buf = torch.zeros(max(self.xplan.S_total, 1) * ROW, dtype=torch.float32, device=dev)
+        self._send = [torch.empty(rows.numel(), ROW, dtype=torch.float32, device=dev) for _, rows in (plan.peers or [])]
+        self._recv = [torch.empty_like(s) for s in self._send]
         self.residuals = torch.zeros(12, dtype=torch.float64, device=dev)
         self.pen_sums = torch.zeros(6, dtype=torch.float64, device=dev)
         self.fused_sums = torch.zeros(6, dtype=torch.float64, device=dev)
@@ -162,11 +223,13 @@ class AdmmBlock:
     def consensus(self, adapt: bool = True):
         """One consensus round: steps (2)-(6) of master_gaussian_trainer.train_iteration."""
         x = [t.detach() for t in self.x]
-        self.ops.pack(x, self.plan, self.buf)
-        if self._world() > 1 and self.plan.S_total > 0:
+        self.ops.pack(x, self.xplan, self.buf)
+        if self.neighbour:
+            self._exchange_with_peers()
+        elif self._world() > 1 and self.plan.S_total > 0:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
         self.residuals.zero_()
-        self.ops.unpack_update(x, self.u, self.z, self.plan, self.buf, self.relax, self.residuals, self.zmu)
+        self.ops.unpack_update(x, self.u, self.z, self.xplan, self.buf, self.relax, self.residuals, self.zmu)
         res = self.residuals.clone()
         # primal_g = sum_k mse(z[idx_k], x_k): every block divides by its own element count
         n = self.plan.n_local
@@ -185,6 +248,21 @@ class AdmmBlock:
                 elif dual[g] > self.mu * primal[g]:
                     self.rho[g] /= self.tau_dec
         return primal, dual
+
+    def _exchange_with_peers(self):
+        """buf[row] += the same Gaussian's parameters from every other owner: one send + one receive per
+        co-owning rank (batched point-to-point), instead of an all-reduce over all shared Gaussians."""
+        rows = self.buf.view(-1, ROW)
+        ops = []
+        for (r, idx), s, rv in zip(self.plan.peers, self._send, self._recv):
+            torch.index_select(rows, 0, idx, out=s)                  # before anything is added
+            peer = dist.get_global_rank(self.group, r) if self.group is not None else r
+            ops.append(dist.P2POp(dist.isend, s, peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, rv, peer, self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for (_, idx), rv in zip(self.plan.peers, self._recv):       # fixed peer order => deterministic sums
+            rows.index_add_(0, idx, rv)
 
     def fused_coef(self):
         n = self.plan.n_local

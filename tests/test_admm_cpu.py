@@ -93,13 +93,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, gidx, xs, out):
+def _worker(rank, world, port, gidx, xs, out, exchange):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         n_global = 400
-        plan = A.build_plan(torch.from_numpy(gidx[rank]), n_global)
+        plan = A.build_plan(torch.from_numpy(gidx[rank]), n_global, exchange=exchange)
+        assert (plan.peers is not None) == (exchange == "neighbour")
         blk = A.AdmmBlock([torch.from_numpy(a.copy()) for a in xs[rank]], plan, ops=OracleOps())
         rho0 = list(blk.rho)
         primal, dual = blk.consensus()
@@ -117,12 +118,14 @@ def _worker(rank, world, port, gidx, xs, out):
         dist.destroy_process_group()
 
 
-def test_two_rank_consensus_over_gloo_matches_reference_arithmetic():
-    world = 2
+@pytest.mark.parametrize("world,exchange", [(2, "neighbour"), (3, "neighbour"), (3, "dense")])
+def test_multi_rank_consensus_over_gloo_matches_reference_arithmetic(world, exchange):
+    """world 3: Gaussians owned by three blocks, i.e. rows that receive from two peers.  "neighbour" is the
+    point-to-point exchange with the co-owners only, "dense" the all-reduce over all shared Gaussians."""
     gidx, xs = _problem(world)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), gidx, xs, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), gidx, xs, out, exchange), nprocs=world, join=True)
     n_global = 400
     # reference arithmetic (oracle numpy restatement of master:538-555, slave:99-121, master:396-456)
     z, count = O.admm_consensus(xs, gidx, n_global)
@@ -135,8 +138,8 @@ def test_two_rank_consensus_over_gloo_matches_reference_arithmetic():
     u1 = [O.admm_dual_update(xs[k], [np.zeros_like(a) for a in xs[k]], [zz[gidx[k]] for zz in z], 1.5) for k in range(world)]
     for k in range(world):
         assert np.allclose(out[k]["primal"], primal_ref, rtol=1e-5)
-        assert out[0]["primal"] == out[1]["primal"] and out[0]["dual"] == out[1]["dual"]   # identical on all ranks
-        assert out[0]["rho"] == out[1]["rho"]
+        assert out[0]["primal"] == out[k]["primal"] and out[0]["dual"] == out[k]["dual"]   # identical on all ranks
+        assert out[0]["rho"] == out[k]["rho"]
     # round 2
     xs2 = [[a + np.float32(0.01 * (k + 1)) for a in xs[k]] for k in range(world)]
     z2, _ = O.admm_consensus(xs2, gidx, n_global)
