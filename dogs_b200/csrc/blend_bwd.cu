@@ -17,8 +17,10 @@
 //   * the colour/depth prefix of the reference (ar[3], ard) is carried as ONE scalar
 //     S = sum_c ar_c * dL/dC_c + ard * dL/dD, which removes 3/4 of the per-pair state updates:
 //       dL/dalpha = T * (c . dL/dC + invd * dL/dD) + S / (1 - alpha)  - T_final * bg.dL/dC / (1 - alpha);
-//   * 10 totals reduced with a transposed butterfly (12 shuffles), accumulated per tile in shared
-//     memory, flushed with red.global.add.v4/v2.f32 (3 vector reductions per tile instance).
+//   * 10 totals reduced with a transposed butterfly (12 shuffles), stored per warp in shared memory
+//     (a warp meets an entry once per batch, so no shared atomic is needed), the two half tiles are
+//     summed at the end of the batch and flushed with red.global.add.v4/v2.f32 (3 vector reductions
+//     per tile instance).
 #include "blend_common.cuh"
 
 namespace dogs {

@@ -276,3 +276,25 @@ def select_gaussians_in_each_block(xyz, bboxes, transform_world_to_obb=None):
     assert (visibility != 0).all()
     return valid, visibility, global_indices
 
+
+def l1_ssim_loss(img, gt, lam=0.2):
+    """conerf/trainers/gaussian_trainer.py:403-405: (1-l)*l1_loss(img, gt) + l*(1 - fused_ssim(img, gt)) and its
+    gradient w.r.t. img, composed from the SSIM restatement above.  img, gt: [C,H,W] float32."""
+    a, b = _f32(img)[None], _f32(gt)[None]
+    m, d1, d2, d3 = ssim_fwd(a, b)
+    n = a.size
+    loss = (1.0 - lam) * float(np.abs(a.astype(np.float64) - b).mean()) + lam * (1.0 - float(m.astype(np.float64).mean()))
+    dmap = np.full_like(a, np.float32(-lam) / np.float32(n))
+    grad = ssim_bwd(a, b, dmap, d1, d2, d3) + (np.float32(1.0 - lam) / np.float32(n)) * np.sign(a - b)
+    return loss, grad[0].astype(np.float32)
+
+
+def activations(raw_opacity, raw_scaling, raw_quaternion):
+    """gaussian_splat_model.py:148-153: sigmoid, exp, F.normalize(dim=1, eps=1e-12) in float32."""
+    o = (np.float32(1) / (np.float32(1) + np.exp(-_f32(raw_opacity)))).astype(np.float32)
+    s = np.exp(_f32(raw_scaling)).astype(np.float32)
+    q = _f32(raw_quaternion)
+    sq = q * q
+    nrm = np.sqrt((sq[:, 0] + sq[:, 2]) + (sq[:, 1] + sq[:, 3]))       # torch's row-reduction order
+    return o, s, (q / np.maximum(nrm, np.float32(1e-12))[:, None]).astype(np.float32)
+

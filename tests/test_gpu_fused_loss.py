@@ -54,3 +54,26 @@ def test_fused_loss_upstream_gradient_and_repeat_calls():
         assert U.rel_to_max(gr, a.grad) <= 1e-6
     with torch.no_grad():                            # inference: no derivative maps
         assert abs(fused_l1_ssim_loss(img0, gt).item() - vals[0][0]) <= 1e-7
+
+
+def test_fused_loss_and_activations_against_committed_goldens():
+    """tests/golden/{loss_l1_ssim,activations}.npz were produced by the reference composition
+    (tools/make_golden_loss.py); the CUDA path must reproduce them without the reference present."""
+    import os
+    import numpy as np
+    from dogs_b200 import _lib as L
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "loss_l1_ssim.npz"))
+    img = torch.from_numpy(g["img"]).to(DEV).requires_grad_(True)
+    loss = fused_l1_ssim_loss(img, torch.from_numpy(g["gt"]).to(DEV), float(g["lam"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6
+    assert U.rel_to_max(img.grad, torch.from_numpy(g["grad"]).to(DEV)) <= 1e-6
+    a = np.load(os.path.join(gold, "activations.npz"))
+    raw = [torch.from_numpy(a[k]).to(DEV) for k in ("raw_opacity", "raw_scaling", "raw_quaternion")]
+    out = [torch.empty_like(t) for t in raw]
+    L.check(L.lib().dgr_apply_activations(raw[0].shape[0], *[t.data_ptr() for t in raw], *[t.data_ptr() for t in out],
+                                          L.stream_ptr(torch.device(DEV))))
+    for t, k in zip(out, ("opacity", "scaling", "quaternion")):
+        assert torch.equal(U.bits(t), U.bits(torch.from_numpy(a[k]).to(DEV))), k
+
