@@ -81,6 +81,9 @@ __device__ __forceinline__ int bb_slot(int lane) {
 // global accumulator slots: 0 mean2D.x, 1 mean2D.y, 2 conic.x, 3 conic.y, 4 conic.w, 5 opacity,
 //                           6..8 colour rgb, 9 inverse depth
 // shared (per tile) slots 0..5 hold sum q, q*(dx*cx+dy*cy), q*(dy*cz+dx*cy), q*dx^2, q*dx*dy, q*dy^2 instead
+// HAS_DEPTH = false: no gradient arrives through the inverse-depth image (the usual photometric loss),
+// so the depth terms are compiled out (they would only add exact zeros).
+template <bool HAS_DEPTH>
 __global__ void __launch_bounds__(BB_THREADS)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
                  int H, const float* __restrict__ bg_color, const SplatRecord* __restrict__ rec,
@@ -127,10 +130,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       dC0[k] = dL_dpixels[0 * HW + pix_id];
       dC1[k] = dL_dpixels[1 * HW + pix_id];
       dC2[k] = dL_dpixels[2 * HW + pix_id];
-      dD[k] = dL_invdepths ? dL_invdepths[pix_id] : 0.f;
+      dD[k] = HAS_DEPTH ? dL_invdepths[pix_id] : 0.f;
       // S = sum_c (prefix_c - pixel_c) * dL/dC_c + (prefix_d - pixel_d) * dL/dD, prefix = 0 at the start
       S[k] = -(pixel_colors[0 * HW + pix_id] * dC0[k] + pixel_colors[1 * HW + pix_id] * dC1[k] +
-               pixel_colors[2 * HW + pix_id] * dC2[k] + pixel_invdepths[pix_id] * dD[k]);
+               pixel_colors[2 * HW + pix_id] * dC2[k] + (HAS_DEPTH ? pixel_invdepths[pix_id] * dD[k] : 0.f));
       // backward.cu:604-621: the background term (-T_final/(1-alpha)) * (bg . dL/dC)
       bgT[k] = final_Ts[pix_id] * (bg0 * dC0[k] + bg1 * dC1[k] + bg2 * dC2[k]);
     }
@@ -254,7 +257,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float alpha = c ? al : 0.f;              // masked lanes: weight 0, T and S unchanged
         const float Gk = c ? G : 0.f;                  // (exp(power) may be inf where power > 0)
         // c . dL/dC + invd * dL/dD
-        const float cd = b.w * dC0[k] + cc.x * dC1[k] + cc.y * dC2[k] + invd * dD[k];
+        const float cd = HAS_DEPTH ? b.w * dC0[k] + cc.x * dC1[k] + cc.y * dC2[k] + invd * dD[k]
+                                   : b.w * dC0[k] + cc.x * dC1[k] + cc.y * dC2[k];
         const float Tk = T[k];
         const float weight = alpha * Tk;
         const float om = 1.0f - alpha;
@@ -265,7 +269,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         v[6] += weight * dC0[k];
         v[7] += weight * dC1[k];
         v[8] += weight * dC2[k];
-        v[9] += weight * dD[k];
+        if (HAS_DEPTH) v[9] += weight * dD[k];
         // Only pixel-dependent moments of q = G * dL/dalpha are accumulated here; the per-splat
         // factors (opacity, conic, 0.5*W, 0.5*H) of backward.cu:626-641 are applied once per
         // (tile, splat) when the batch is flushed.
@@ -319,7 +323,13 @@ int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b
                      cudaStream_t s) {
   cudaMemsetAsync(accum, 0, (size_t)prm.P * BB_ACC * sizeof(float), s);
   dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
-  blend_bwd_kernel<<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
+  if (dL_dinvdepth)
+    blend_bwd_kernel<true><<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
+                                               im.final_T, im.n_contrib, im.pix_color,
+                                               im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
+                                               prm.ref_bucket_cull_quirk != 0);
+  else
+    blend_bwd_kernel<false><<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
                                                im.final_T, im.n_contrib, im.pix_color,
                                                im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
                                                prm.ref_bucket_cull_quirk != 0);

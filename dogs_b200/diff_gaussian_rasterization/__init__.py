@@ -197,6 +197,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                               binning.last if binning.last is not None else empty,
                               image.last if image.last is not None else empty)
         ctx.mark_non_differentiable(radii)
+        # an output the loss does not use arrives as None in backward (no zero image is materialised, and
+        # the blend backward compiles its depth terms out)
+        ctx.set_materialize_grads(False)
         return color, radii, invdepth
 
     @staticmethod
