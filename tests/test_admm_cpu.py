@@ -51,7 +51,7 @@ class OracleOps:
                 grads[g] += coef[g] * r
 
 
-def _problem(nblocks, n_global=400, seed=0):
+def _problem(nblocks, n_global=400, seed=0, shuffle=False):
     rng = np.random.default_rng(seed)
     gidx, xs = [], []
     owned = np.zeros(n_global, bool)
@@ -60,6 +60,8 @@ def _problem(nblocks, n_global=400, seed=0):
         gidx.append(idx)
         owned[idx] = True
     gidx[0] = np.sort(np.union1d(gidx[0], np.nonzero(~owned)[0]))
+    if shuffle:          # blocks need not list their Gaussians in ascending global order
+        gidx = [rng.permutation(idx) for idx in gidx]
     for idx in gidx:
         xs.append([rng.standard_normal((len(idx), sz)).astype(np.float32) for sz in O.GROUP_SIZES])
     return gidx, xs
@@ -118,11 +120,12 @@ def _worker(rank, world, port, gidx, xs, out, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,exchange", [(2, "neighbour"), (3, "neighbour"), (3, "dense")])
-def test_multi_rank_consensus_over_gloo_matches_reference_arithmetic(world, exchange):
+@pytest.mark.parametrize("world,exchange,shuffle", [(2, "neighbour", False), (3, "neighbour", False),
+                                                    (3, "neighbour", True), (3, "dense", False)])
+def test_multi_rank_consensus_over_gloo_matches_reference_arithmetic(world, exchange, shuffle):
     """world 3: Gaussians owned by three blocks, i.e. rows that receive from two peers.  "neighbour" is the
     point-to-point exchange with the co-owners only, "dense" the all-reduce over all shared Gaussians."""
-    gidx, xs = _problem(world)
+    gidx, xs = _problem(world, shuffle=shuffle)
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), gidx, xs, out, exchange), nprocs=world, join=True)
