@@ -184,10 +184,9 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     uint32_t* total = cv.take<uint32_t>(1);
     char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(P));
     char* scan_scratch = cv.take<char>(scan_scratch_bytes(P));
-    launch_iota(g.sorted_idx, P, s);
     int in_b = 0;
     // 4 passes of 8 bits => the result is back in (depth_key, sorted_idx)
-    if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b)) return 1;
+    if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b, true)) return 1;
     if (in_b) cudaMemcpyAsync(g.sorted_idx, vals_b, P * 4, cudaMemcpyDeviceToDevice, s);
     // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
     // the scan and the emit kernel then stream sequentially

@@ -95,7 +95,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   for (int s = 0; s < SORT_ITEMS; s++) {
     uint32_t idx = wbase + s * 32 + lane;
     key[s] = idx < n ? keys_in[idx] : 0u;
-    val[s] = idx < n ? vals_in[idx] : 0u;
+    val[s] = idx < n ? (vals_in ? vals_in[idx] : idx) : 0u;   // null vals_in: the values are the indices
   }
 
   // global digit base = exclusive scan of the digit totals (thread d owns digit d)
@@ -200,7 +200,7 @@ size_t sort_pairs_scratch_bytes(size_t n) {
 
 int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                    size_t n, int begin_bit, int end_bit, char* scratch, bool debug,
-                   cudaStream_t s, int* result_in_b) {
+                   cudaStream_t s, int* result_in_b, bool vals_are_iota) {
   *result_in_b = 0;
   if (n == 0 || end_bit <= begin_bit) return 0;
   uint32_t nblk = (uint32_t)((n + SORT_CHUNK - 1) / SORT_CHUNK);
@@ -213,8 +213,8 @@ int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_
     uint32_t mask = (1u << nb) - 1u;
     radix_hist_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, (uint32_t)n, b, mask, hist, nblk);
     radix_rowscan_kernel<<<RADIX, 256, 0, s>>>(hist, nblk, totals);
-    radix_scatter_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, vi, ko, vo, (uint32_t)n, b, mask, hist,
-                                                      nblk, totals);
+    radix_scatter_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, (vals_are_iota && b == begin_bit) ? nullptr : vi, ko, vo,
+                                                      (uint32_t)n, b, mask, hist, nblk, totals);
     if (int e = check_launch("radix pass", debug, s, 3)) return e;
     uint32_t* t;
     t = ki; ki = ko; ko = t;
