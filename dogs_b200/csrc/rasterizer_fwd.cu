@@ -386,21 +386,33 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
 }
 
 // identifyTileRanges (rasterizer_impl.cu:195-220) on 32-bit tile keys; no pad entries exist.
+// Four consecutive keys per thread (one 16-byte load + the predecessor).
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys, uint2* __restrict__ ranges) {
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L) return;
-  uint32_t cur = tile_keys[idx];
-  if (idx == 0)
-    ranges[cur].x = 0;
-  else {
-    uint32_t prev = tile_keys[idx - 1];
-    if (cur != prev) {
+  const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (i0 >= L) return;
+  const uint32_t n = min(4u, L - i0);
+  uint32_t k[4] = {0u, 0u, 0u, 0u};
+  if (n == 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + i0);
+    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+  } else {
+    for (uint32_t q = 0; q < n; q++) k[q] = tile_keys[i0 + q];
+  }
+  uint32_t prev = i0 ? tile_keys[i0 - 1] : 0u;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; q++) {
+    if (q >= n) break;
+    const uint32_t idx = i0 + q, cur = k[q];
+    if (idx == 0) {
+      ranges[cur].x = 0;
+    } else if (cur != prev) {
       ranges[prev].y = idx;
       ranges[cur].x = idx;
     }
+    if (idx == L - 1) ranges[cur].y = L;
+    prev = cur;
   }
-  if (idx == L - 1) ranges[cur].y = L;
 }
 
 // ---- visible_filter / mark_visible ---------------------------------------------------
@@ -507,7 +519,7 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_ke
                        cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
-  if (R > 0) tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, tile_keys, ranges);
+  if (R > 0) tile_ranges_kernel<<<(R + 1023) / 1024, 256, 0, s>>>(R, tile_keys, ranges);
   return check_launch("tile_ranges", prm.debug != 0, s);
 }
 
