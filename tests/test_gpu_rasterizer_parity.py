@@ -313,7 +313,7 @@ def test_mixed_rect_sizes_vs_reference(P):
         assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, k
 
 
-@pytest.mark.parametrize("cfg", ["C3"])
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
 def test_full_size_properties(cfg):
     """BASELINE.json's headline size: exact forward parity with the reference plus
     size-independent properties (sortedness, range partition, idempotence, linearity)."""
