@@ -218,7 +218,6 @@ size_t sort_pairs_scratch_bytes(size_t n);
 int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                    size_t n, int begin_bit, int end_bit, char* scratch, bool debug, cudaStream_t s,
                    int* result_in_b, bool vals_are_iota = false);   // true: vals_a is treated as 0..n-1 and never read
-void launch_iota(uint32_t* out, size_t n, cudaStream_t s);
 size_t scan_scratch_bytes(size_t n);
 // out[i] = sum_{j<i} in[idx ? idx[j] : j]; total (may be null) receives the grand total.
 int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* total,

@@ -181,17 +181,6 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
 }
 
-__global__ void iota_kernel(uint32_t* out, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i;
-}
-void launch_iota(uint32_t* out, size_t n, cudaStream_t s) {
-  if (n) {
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, (uint32_t)n);
-    check_launch("iota", false, s);
-  }
-}
-
 size_t sort_pairs_scratch_bytes(size_t n) {
   size_t nblk = (n + SORT_CHUNK - 1) / SORT_CHUNK;
   if (nblk == 0) nblk = 1;
