@@ -78,8 +78,10 @@ SIGNATURES = {
     "fssim_l1_loss_backward": [C.c_int32] * 4 + [C.c_float] * 2 + [_P] * 5 + [_P, _P, _P],
     "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],
     "admm_block_membership": [C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P],
-    "admm_pack": [C.POINTER(AdmmTensors), _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P],
-    "admm_unpack_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, _P, C.c_int64, _P, C.c_float, _P, _P],
+    "admm_pack_rows": [C.POINTER(AdmmTensors), _P, C.c_int64, _P, _P],
+    "admm_consensus_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, _P, _P, C.c_int32, C.c_int64,
+                                                             C.POINTER(C.c_void_p), C.c_int32, C.c_float, _P, _P, _P],
+    "admm_consensus_scratch_bytes": [],
     "admm_penalty": [C.POINTER(AdmmTensors)] * 3 + [_P, C.c_int64, _P, _P, _P],
     "dogs_last_error": [],
     "dogs_abi_version": [],
@@ -104,6 +106,7 @@ def lib():
             fn.restype = C.c_int
         _lib.dogs_last_error.restype = C.c_char_p
         _lib.dogs_launch_count.restype = C.c_ulonglong
+        _lib.admm_consensus_scratch_bytes.restype = C.c_size_t
     return _lib
 
 

@@ -1,10 +1,11 @@
 // ADMM Gaussian-consensus kernels.  They replace the torch tensor arithmetic of
 //   master_gaussian_trainer.py:538-555 (consensus average), :396-456 (primal/dual residuals),
 //   slave_gaussian_trainer.py:99-121 (dual update) and :161-202 (penalty terms)
-// for one scene block per GPU.  Only Gaussians owned by more than one block travel: they are
-// packed into a dense [S_total, 59] buffer, summed across ranks with ONE NCCL all-reduce, and
-// unpacked by kernels that also apply the dual update and accumulate the residual sums, so the
-// 59 floats of a Gaussian are read and written once per consensus round.
+// for the scene blocks of one GPU.  Only Gaussians owned by more than one block travel: one launch packs
+// them as 59-float rows straight into the per-co-owner exchange buffers, and after the exchange one
+// launch averages (in the reference's block order, so z is bit-identical to the master's), applies
+// the dual update and accumulates the residual sums: the 59 floats of a Gaussian are read and written
+// once per consensus round.
 //
 // A Gaussian = 59 floats in 6 tensors: xyz 3, f_dc 3, f_rest 45, scaling 3, quaternion 4, opacity 1
 // (raw, pre-activation values are the consensus variables).
@@ -89,71 +90,143 @@ admm_penalty_kernel(const __grid_constant__ PenaltyArgs a, double* __restrict__ 
   if (threadIdx.x < 6 && acc[threadIdx.x] != 0.0) atomicAdd(&sums[threadIdx.x], acc[threadIdx.x]);
 }
 
-// sendbuf[slot[i]*59 + START + off] = x[local_idx[i]*SZ + off], flat over the S*SZ elements of one group
-template <int SZ>
+// ---- consensus round: two launches per block --------------------------------------------------------
+// Work layout shared by both kernels: one warp per Gaussian row, lane l owns elements l and l + 32 of
+// the 59-float row, so the consensus group of a lane (xyz / f_dc / f_rest / scaling / quaternion /
+// opacity) is FIXED: no per-element division, the per-group residual sums stay in registers, and
+// every exchange-buffer row is read / written as 236 contiguous bytes.
+struct RowLane {
+  int g[2], off[2], sz[2];   // tensor, offset in the tensor's row, row length; g = -1: lane has no 2nd element
+};
+__device__ __forceinline__ RowLane row_lane(int lane) {
+  RowLane r;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int e = lane + 32 * h;
+    int g, off, sz;
+    if (e < 3) { g = 0; off = e; sz = 3; }
+    else if (e < 6) { g = 1; off = e - 3; sz = 3; }
+    else if (e < 51) { g = 2; off = e - 6; sz = 45; }
+    else if (e < 54) { g = 3; off = e - 51; sz = 3; }
+    else if (e < 58) { g = 4; off = e - 54; sz = 4; }
+    else if (e < 59) { g = 5; off = 0; sz = 1; }
+    else { g = -1; off = 0; sz = 0; }
+    r.g[h] = g; r.off[h] = off; r.sz[h] = sz;
+  }
+  return r;
+}
+
+struct PackArgs { const float* x[6]; };
+
+// out[r*59 + e] = x[src_local[r]][e] for the R rows this block sends to its co-owners (rows of all peers
+// concatenated; a Gaussian shared with three other blocks appears three times).  Replaces the six
+// per-tensor gathers + one torch.index_select per peer of the first version.
 __global__ void __launch_bounds__(ADMM_THREADS)
-admm_pack_kernel(const float* __restrict__ x, const int64_t* __restrict__ local_idx,
-                 const int64_t* __restrict__ slot, unsigned long long total, int start,
-                 float* __restrict__ sendbuf) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const unsigned long long i = e / SZ;
-    const int off = (int)(e - i * SZ);
-    sendbuf[slot[i] * ADMM_ROW + start + off] = x[local_idx[i] * SZ + off];
+admm_pack_rows_kernel(const __grid_constant__ PackArgs a, const int32_t* __restrict__ src_local,
+                      int64_t R, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const RowLane rl = row_lane(lane);
+  const float* p0 = a.x[rl.g[0]];
+  const float* p1 = rl.g[1] >= 0 ? a.x[rl.g[1]] : nullptr;
+  const int64_t nwarps = (int64_t)gridDim.x * (ADMM_THREADS / 32);
+  for (int64_t r = (int64_t)blockIdx.x * (ADMM_THREADS / 32) + (threadIdx.x >> 5); r < R; r += nwarps) {
+    const int64_t li = src_local[r];
+    const float v0 = __ldg(p0 + li * rl.sz[0] + rl.off[0]);
+    float v1 = 0.f;
+    if (p1) v1 = __ldg(p1 + li * rl.sz[1] + rl.off[1]);
+    out[r * ADMM_ROW + lane] = v0;
+    if (p1) out[r * ADMM_ROW + 32 + lane] = v1;
   }
 }
 
-// Over ALL n Gaussians of the block (flat over n*SZ elements of one group):
-//   shared (slot >= 0): z = recv * inv_count (master:551-555); u += relax*(x - z) (slave:99-121)
-//   single-owner      : z = x, u untouched
-//   residuals[g] += sum (z - x)^2 (primal, master:396-432); residuals[6+g] += sum inv_count*(z_prev - z)^2 (dual, :435-456)
-template <int SZ>
+constexpr int ADMM_MAX_SOURCES = 16;
+struct ConsensusArgs {
+  const float* x[6];
+  float* u[6];
+  float* z[6];
+  float* zmu[6];                        // nullable (all or none)
+  const float* src[ADMM_MAX_SOURCES];   // exchange buffers [rows, 59] the addends come from
+};
+
+// Over ALL n Gaussians of the block:
+//   shared (shared_row[i] >= 0): z = (a_0 + a_1 + ...) / count with the addends in ASCENDING BLOCK ORDER
+//       (plus_gaussians over k = 0..K-1, then average_gaussians: gaussian_splat_model.py:325-340 called
+//       from master_gaussian_trainer.py:549-555), each addend either this block's own x or a row of a
+//       co-owner's exchange buffer; true IEEE division by the count;
+//       u += relax * (x - z) rounded like torch's three separate ops (slave_gaussian_trainer.py:99-121);
+//   single owner: z = x, u unchanged (the reference adds relax * 0).
+//   zmu = z - u for the per-iteration penalty.  Residual sums in FP64: partial[blk][g] = sum (z - x)^2
+//   (primal, master:396-432), partial[blk][6+g] = sum (z_prev - z)^2 / count (dual, master:435-456: every
+//   global Gaussian once); the last CTA to finish folds the partials in a fixed order into residuals[12].
 __global__ void __launch_bounds__(ADMM_THREADS)
-admm_unpack_kernel(const float* __restrict__ x, float* __restrict__ u, float* __restrict__ z,
-                   float* __restrict__ zmu, const int64_t* __restrict__ slot_of_local, const float* __restrict__ inv_count,
-                   unsigned long long total, int start, const float* __restrict__ recvbuf, float relax,
-                   double* __restrict__ residuals, int g) {
-  __shared__ double acc[2];
-  if (threadIdx.x < 2) acc[threadIdx.x] = 0.0;
+admm_consensus_kernel(const __grid_constant__ ConsensusArgs a, const int32_t* __restrict__ shared_row,
+                      const uint32_t* __restrict__ addends, const uint8_t* __restrict__ count, int max_addends,
+                      int64_t n, float relax, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                      double* __restrict__ residuals) {
+  __shared__ double acc[12];
+  __shared__ bool last;
+  if (threadIdx.x < 12) acc[threadIdx.x] = 0.0;
   __syncthreads();
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  double primal = 0.0, dual = 0.0;
-  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const unsigned long long i = e / SZ;
-    const int off = (int)(e - i * SZ);
-    const int64_t sl = slot_of_local[i];
-    const float xv = x[e];
-    const float z_old = z[e];
-    float z_new;
-    if (sl >= 0) {
-      const float w = inv_count[i];
-      z_new = recvbuf[sl * ADMM_ROW + start + off] * w;
-      const float u_new = u[e] + relax * (xv - z_new);
-      u[e] = u_new;
-      if (zmu) zmu[e] = z_new - u_new;
-      const float dp = z_new - xv;
-      primal += (double)dp * dp;
-      const float dd = z_old - z_new;
-      dual += (double)w * ((double)dd * dd);
-    } else {
-      z_new = xv;
-      const float dd = z_old - z_new;
-      dual += (double)dd * dd;
-      if (zmu) zmu[e] = z_new - u[e];
+  const int lane = threadIdx.x & 31;
+  const RowLane rl = row_lane(lane);
+  const bool has_zmu = a.zmu[0] != nullptr;
+  double primal[2] = {0.0, 0.0}, dual[2] = {0.0, 0.0};
+  const int64_t nwarps = (int64_t)gridDim.x * (ADMM_THREADS / 32);
+  for (int64_t i = (int64_t)blockIdx.x * (ADMM_THREADS / 32) + (threadIdx.x >> 5); i < n; i += nwarps) {
+    const int32_t sr = shared_row[i];
+    float cnt = 1.f;
+    if (sr >= 0) cnt = (float)count[sr];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (rl.g[h] < 0) continue;
+      const int g = rl.g[h];
+      const int64_t e = i * rl.sz[h] + rl.off[h];
+      const float xv = a.x[g][e];
+      const float z_old = a.z[g][e];
+      float u_new = a.u[g][e];
+      float z_new = xv;
+      if (sr >= 0) {
+        float s = 0.f;
+        for (int j = 0; j < max_addends; j++) {
+          const uint32_t ent = addends[(int64_t)sr * max_addends + j];
+          if (ent == 0xffffffffu) break;
+          const uint32_t which = ent >> 28;
+          const float v = which == 15u ? xv
+                                       : __ldg(a.src[which] + (int64_t)(ent & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
+          s = j == 0 ? v : __fadd_rn(s, v);
+        }
+        z_new = __fdiv_rn(s, cnt);
+        u_new = __fadd_rn(u_new, __fmul_rn(relax, __fsub_rn(xv, z_new)));
+        a.u[g][e] = u_new;
+      }
+      a.z[g][e] = z_new;
+      if (has_zmu) a.zmu[g][e] = z_new - u_new;
+      const double dp = (double)z_new - (double)xv, dd = (double)z_old - (double)z_new;
+      primal[h] += dp * dp;
+      dual[h] += dd * dd / (double)cnt;
     }
-    z[e] = z_new;
   }
-  block_sum_to(primal, &acc[0]);
-  block_sum_to(dual, &acc[1]);
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    if (rl.g[h] < 0) continue;
+    if (primal[h] != 0.0) atomicAdd(&acc[rl.g[h]], primal[h]);
+    if (dual[h] != 0.0) atomicAdd(&acc[6 + rl.g[h]], dual[h]);
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (acc[0] != 0.0) atomicAdd(&residuals[g], acc[0]);
-    if (acc[1] != 0.0) atomicAdd(&residuals[6 + g], acc[1]);
+  if (threadIdx.x < 12) partial[(size_t)blockIdx.x * 12 + threadIdx.x] = acc[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < 12) {
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; b++) t += __ldcg(&partial[(size_t)b * 12 + threadIdx.x]);
+    residuals[threadIdx.x] += t;
+    if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
 static const int kSize[6] = {3, 3, 45, 3, 4, 1};
-static const int kStart[6] = {0, 3, 6, 51, 54, 58};
 
 static int grid_for(unsigned long long work_items) {
   unsigned long long g = (work_items + ADMM_THREADS - 1) / ADMM_THREADS;
@@ -165,34 +238,50 @@ static int grid_for(unsigned long long work_items) {
 
 using namespace dogs;
 
-extern "C" int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, const int64_t* slot,
-                         int64_t S, int64_t S_total, int32_t zero_fill, float* sendbuf, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!sendbuf && S_total > 0) { set_error("admm_pack: null send buffer"); return 1; }
-  if (zero_fill && S_total > 0) cudaMemsetAsync(sendbuf, 0, (size_t)S_total * ADMM_ROW * sizeof(float), s);
-  if (S <= 0) return check_launch("admm_pack", false, s, 0);
-  if (!x || !local_idx || !slot) { set_error("admm_pack: null pointer"); return 1; }
-#define PACK(G, SZ)                                                                                   \
-  admm_pack_kernel<SZ><<<grid_for((unsigned long long)S * SZ), ADMM_THREADS, 0, s>>>(                 \
-      x->g[G], local_idx, slot, (unsigned long long)S * SZ, kStart[G], sendbuf)
-  PACK(0, 3); PACK(1, 3); PACK(2, 45); PACK(3, 3); PACK(4, 4); PACK(5, 1);
-#undef PACK
-  return check_launch("admm_pack", false, s, 6);
+static int consensus_grid(int64_t rows) {
+  const int64_t per_cta = ADMM_THREADS / 32;
+  int64_t g = (rows + per_cta - 1) / per_cta;
+  const int64_t cap = 148 * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-extern "C" int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
-                                  const AdmmTensors* zmu, const int64_t* slot_of_local, const float* inv_count, int64_t n,
-                                  const float* recvbuf, float relax, double* residuals, void* stream) {
+extern "C" size_t admm_consensus_scratch_bytes(void) { return (size_t)(148 * 8) * 12 * sizeof(double) + 256; }
+
+extern "C" int admm_pack_rows(const AdmmConstTensors* x, const int32_t* src_local, int64_t R, float* out,
+                              void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R <= 0) return 0;
+  if (!x || !src_local || !out) { set_error("admm_pack_rows: null pointer"); return 1; }
+  PackArgs a;
+  for (int g = 0; g < 6; g++) {
+    a.x[g] = x->g[g];
+    if (!a.x[g]) { set_error("admm_pack_rows: null tensor"); return 1; }
+  }
+  admm_pack_rows_kernel<<<consensus_grid(R), ADMM_THREADS, 0, s>>>(a, src_local, R, out);
+  return check_launch("admm_pack_rows", false, s);
+}
+
+extern "C" int admm_consensus_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
+                                     const AdmmTensors* zmu, const int32_t* shared_row, const uint32_t* addends,
+                                     const uint8_t* count, int32_t max_addends, int64_t n,
+                                     const float* const* sources, int32_t n_sources, float relax,
+                                     void* scratch, double* residuals, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 0) return 0;
-  if (!x || !u || !z || !slot_of_local || !inv_count || !residuals) { set_error("admm_unpack_update: null pointer"); return 1; }
-#define UNPACK(G, SZ)                                                                                 \
-  admm_unpack_kernel<SZ><<<grid_for((unsigned long long)n * SZ), ADMM_THREADS, 0, s>>>(               \
-      x->g[G], u->g[G], z->g[G], zmu ? zmu->g[G] : nullptr, slot_of_local, inv_count, (unsigned long long)n * SZ, kStart[G], recvbuf, \
-      relax, residuals, G)
-  UNPACK(0, 3); UNPACK(1, 3); UNPACK(2, 45); UNPACK(3, 3); UNPACK(4, 4); UNPACK(5, 1);
-#undef UNPACK
-  return check_launch("admm_unpack_update", false, s, 6);
+  if (!x || !u || !z || !shared_row || !residuals || !scratch) { set_error("admm_consensus_update: null pointer"); return 1; }
+  if (n_sources < 0 || n_sources > ADMM_MAX_SOURCES - 1) { set_error("admm_consensus_update: at most %d exchange buffers", ADMM_MAX_SOURCES - 1); return 1; }
+  if (max_addends > 0 && (!addends || !count)) { set_error("admm_consensus_update: null addend table"); return 1; }
+  ConsensusArgs a;
+  for (int g = 0; g < 6; g++) {
+    a.x[g] = x->g[g]; a.u[g] = u->g[g]; a.z[g] = z->g[g]; a.zmu[g] = zmu ? zmu->g[g] : nullptr;
+    if (!a.x[g] || !a.u[g] || !a.z[g]) { set_error("admm_consensus_update: null tensor"); return 1; }
+  }
+  for (int k = 0; k < ADMM_MAX_SOURCES; k++) a.src[k] = (sources && k < n_sources) ? sources[k] : nullptr;
+  double* partial = reinterpret_cast<double*>(scratch);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(scratch) + (size_t)(148 * 8) * 12 * sizeof(double));
+  admm_consensus_kernel<<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
+                                                                  relax, partial, ticket, residuals);
+  return check_launch("admm_consensus_update", false, s);
 }
 
 extern "C" int admm_penalty(const AdmmConstTensors* x, const AdmmConstTensors* u, const AdmmConstTensors* z,

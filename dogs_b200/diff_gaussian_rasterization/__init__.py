@@ -45,23 +45,17 @@ class GaussianRasterizationSettings(NamedTuple):  # reference __init__.py:203-21
     # (gaussian_splat_model.py:148-153) run inside preprocess and the returned gradients are w.r.t. the
     # raw tensors, replacing three torch activation kernels and their three backward kernels per render.
     raw_activations: bool = False
+    # Extension: fused ADMM penalty (slave_gaussian_trainer.py:161-202).  A dogs_b200.admm.AdmmBlock (any object
+    # with zmu: 6 tensors, fused_coef(): 6 floats, fused_sums: double[6] device tensor, fused_all: bool).  The
+    # backward of THIS render adds coef_g * (x_g - zmu_g) to the gradients of means3D / dc / sh — and of scales /
+    # rotations / opacities when the block was fused with all_groups=True, which requires raw_activations — so
+    # the rasterizer must be fed the block's own parameter tensors (conerf's render() does,
+    # gaussian_render.py:67-110).  Attach it to exactly one render per iteration: the penalty is added per call.
+    admm: object = None
 
 
 def cpu_deep_copy_tuple(input_tuple):
     return tuple(i.cpu().clone() if isinstance(i, torch.Tensor) else i for i in input_tuple)
-
-
-# Optional fused ADMM penalty: an object with attributes zmu (list of 6 tensors, groups xyz, f_dc,
-# f_rest first), coef (6 floats) and fused_sums (double[3] device tensor); see dogs_b200.admm.AdmmBlock.
-# When set, the rasterizer backward adds coef_g * (x_g - zmu_g) to the gradients of means3D / dc / sh
-# (include/dogs_b200.h DgrAdmmPenalty).  The rasterizer must then be fed the block's raw xyz / f_dc /
-# f_rest parameters, which is what conerf's render() does (gaussian_render.py:67-110).
-_FUSED_ADMM = None
-
-
-def set_fused_admm(block):
-    global _FUSED_ADMM
-    _FUSED_ADMM = block
 
 
 def _params(rs, P, M, device, backward=False):
@@ -76,8 +70,12 @@ def _params(rs, P, M, device, backward=False):
         bg=keep[0].data_ptr(), viewmatrix=keep[1].data_ptr(), projmatrix=keep[2].data_ptr(),
         campos=keep[3].data_ptr(), ref_bucket_cull_quirk=int(bool(REFERENCE_BACKWARD_QUIRK)),
         raw_inputs=int(bool(getattr(rs, "raw_activations", False))))
-    blk = _FUSED_ADMM
-    if backward and blk is not None:
+    blk = getattr(rs, "admm", None)
+    if backward and blk is not None and getattr(blk, "fused", True):
+        if blk.fused_all and not getattr(rs, "raw_activations", False):
+            raise RuntimeError("fused ADMM penalty with all_groups=True needs raw_activations=True: the penalty of "
+                               "scaling / quaternion / opacity is taken on the tensors passed to the rasterizer, "
+                               "which must be the raw consensus variables")
         zx, zd, zs = blk.zmu[0], blk.zmu[1], blk.zmu[2]
         if zx.numel() != 3 * P or zd.numel() != 3 * P or (M > 0 and zs.numel() != 3 * M * P):
             raise RuntimeError("fused ADMM penalty: the block's tensors do not match the rasterized Gaussians")

@@ -104,7 +104,8 @@ def make_scene(cfg="C1", seed=0, device="cpu", P=None, sh_degree=3):
 
 
 def raster_settings(mod, scene, bg=None, antialiasing=False, depth_threshold=0.0, debug=False,
-                    scale_modifier=1.0):
+                    scale_modifier=1.0, **extensions):
+    """extensions: fields only this package's settings have (raw_activations, admm, f_count)."""
     dev = scene["means3D"].device
     if bg is None:
         bg = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -113,7 +114,7 @@ def raster_settings(mod, scene, bg=None, antialiasing=False, depth_threshold=0.0
         tanfovy=scene["tanfovy"], bg=bg, scale_modifier=scale_modifier,
         viewmatrix=scene["viewmatrix"], projmatrix=scene["projmatrix"],
         sh_degree=int(scene["sh_degree"]), campos=scene["campos"], prefiltered=False, debug=debug,
-        antialiasing=antialiasing, depth_threshold=depth_threshold)
+        antialiasing=antialiasing, depth_threshold=depth_threshold, **extensions)
 
 
 def render(mod, scene, params=None, **kw):

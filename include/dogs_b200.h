@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DOGS_B200_ABI_VERSION 1
+#define DOGS_B200_ABI_VERSION 2
 
 /* Allocation callback: must return a device pointer to >= bytes bytes, aligned to
  * 256 B, valid until the caller decides to free it.  Mirrors resizeFunctional()
@@ -226,19 +226,33 @@ int sknn_dist2(int32_t P, const float* points, float* mean_dist2,
 typedef struct AdmmTensors { float* g[ADMM_GROUPS]; } AdmmTensors;
 typedef struct AdmmConstTensors { const float* g[ADMM_GROUPS]; } AdmmConstTensors;
 
-/* pack: sendbuf[slot[i]*59 + :] = x[local_idx[i]] for the S shared Gaussians of this block;
- * zero_fill != 0 first clears the whole [S_total,59] buffer (rows owned by other blocks stay 0). */
-int admm_pack(const AdmmConstTensors* x, const int64_t* local_idx, const int64_t* slot,
-              int64_t S, int64_t S_total, int32_t zero_fill, float* sendbuf, void* stream);
-/* unpack_update after the all-reduce(sum), over ALL n Gaussians of the block.
- * slot_of_local[i] >= 0 (shared): z = recv[slot]*inv_count[i]; u += relax*(x - z);
- * slot_of_local[i] <  0 (owned by this block only): z = x, u untouched (master:551-555 with count 1).
- * residuals (device double[12]) is ACCUMULATED: [0..5] sum((z-x)^2) per group (primal, master:396-432),
- * [6..11] sum(inv_count*(z_prev-z)^2) per group (dual, master:435-456; each global Gaussian once). */
-int admm_unpack_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
-                       const AdmmTensors* zmu /* nullable: receives z - u for the penalty fast path */,
-                       const int64_t* slot_of_local, const float* inv_count, int64_t n,
-                       const float* recvbuf, float relax, double* residuals, void* stream);
+/* One consensus round of a block = admm_pack_rows -> exchange of the rows with the co-owning blocks
+ * (NCCL send/recv between GPUs, nothing at all between blocks of the same GPU: the receiver reads the
+ * sender's buffer) -> admm_consensus_update.  Replaces send_local_model / gaussian_splat_consensus /
+ * broadcast_global_gaussian_splat / update_dual_variables / compute_primal_residual /
+ * compute_dual_residual (master_gaussian_trainer.py:396-456,523-555; slave_gaussian_trainer.py:66-71,99-121)
+ * for the Gaussians of one block.
+ *
+ * pack_rows: out[r*59 + :] = the 59 parameters of local Gaussian src_local[r], r < R (the rows for all
+ * co-owners concatenated, each co-owner's rows ordered by global index). */
+int admm_pack_rows(const AdmmConstTensors* x, const int32_t* src_local, int64_t R, float* out, void* stream);
+/* consensus_update over ALL n Gaussians of the block.
+ *   shared_row[i] < 0: owned by this block only: z = x, u untouched (the reference's average with count 1).
+ *   shared_row[i] = s: z = (sum of the addends of row s) / count[s]; u += relax * (x - z).
+ *     addends[s*max_addends + j], j < max_addends, terminated by 0xffffffff: bits 31..28 = 15 -> this block's
+ *     own x, else index into sources[]; bits 27..0 = row of that exchange buffer.  The addends are summed in
+ *     the order listed; listing the owners in ascending block order reproduces the reference's
+ *     plus_gaussians loop + average_gaussians (gaussian_splat_model.py:325-340) bit for bit.
+ *   zmu (nullable) receives z - u for the per-iteration penalty.
+ *   residuals (device double[12]) is ACCUMULATED: [0..5] sum (z-x)^2 per group (primal, master:396-432),
+ *   [6..11] sum (z_prev-z)^2 / count (dual, master:435-456: every global Gaussian counted once over its owners).
+ *   scratch: admm_consensus_scratch_bytes() of device memory, zeroed once by the caller (left zeroed). */
+size_t admm_consensus_scratch_bytes(void);
+int admm_consensus_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,
+                          const AdmmTensors* zmu /* nullable */, const int32_t* shared_row,
+                          const uint32_t* addends, const uint8_t* count, int32_t max_addends, int64_t n,
+                          const float* const* sources /* host array of device pointers */, int32_t n_sources,
+                          float relax, void* scratch, double* residuals, void* stream);
 /* penalty (slave:161-202): sums[g] += sum((x_g+u_g-z_g)^2) (device double[6]); u == NULL means that
  * `z` already holds z - u (the zmu tensors of admm_unpack_update: one pass less per iteration); if grad != NULL,
  * grad_g += coef[g]*(x_g+u_g-z_g) with coef[g] = rho_g/numel_g (host float[6]) — the gradient of

@@ -193,7 +193,8 @@ def sparse_adam(param, grad, m, v, visible, lr, b1, b2, eps):
                           C.c_float(b1), C.c_float(b2), C.c_float(eps), C.c_uint32(N), C.c_uint32(M))
 
 
-# ---- ADMM (numpy restatement of the reference's torch arithmetic) -------------------------------
+# ---- ADMM (numpy restatement of the reference's torch arithmetic; pinned by tests/golden/admm.npz, which
+# tools/make_golden_admm.py produced by executing the reference's own master / slave methods) ----------
 GROUPS = ("xyz", "fdc", "fr", "s", "q", "o")
 GROUP_SIZES = (3, 3, 45, 3, 4, 1)
 

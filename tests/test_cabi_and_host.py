@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "dogs_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+char\s*\*|unsigned\s+long\s+long|int)\s+(\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+char\s*\*|unsigned\s+long\s+long|size_t|int)\s+(\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 
@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dogs_b200.h but not exported"
     assert set(_lib.SIGNATURES) <= set(names), set(_lib.SIGNATURES) - set(names)
-    assert lib.dogs_abi_version() == 1
+    assert lib.dogs_abi_version() == 2
     assert lib.dogs_last_error() is not None
 
 
@@ -97,9 +97,11 @@ def test_settings_fields_match_reference_api():
     assert dgr.GaussianRasterizationSettings._fields == (
         "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
         "sh_degree", "campos", "prefiltered", "debug", "antialiasing", "depth_threshold", "f_count",
-        "raw_activations")
+        "raw_activations", "admm")
     # the reference's 14 fields come first and in its order; the extensions are defaulted
     assert dgr.GaussianRasterizationSettings._field_defaults["raw_activations"] is False
+    assert dgr.GaussianRasterizationSettings._field_defaults["admm"] is None
+    assert not hasattr(dgr, "set_fused_admm")          # no module-level ADMM state
     import inspect
     sig = inspect.signature(dgr.GaussianRasterizer.forward)
     assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "dc", "shs", "colors_precomp", "scales",

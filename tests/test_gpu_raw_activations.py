@@ -30,10 +30,10 @@ def _raw_scene(cfg, seed):
     return raw
 
 
-def _render(raw, fused, antialiasing, leaves):
+def _render(raw, fused, antialiasing, leaves, admm=None):
     rs = scenes.raster_settings(dgr, raw, antialiasing=antialiasing)
     if fused:
-        rs = rs._replace(raw_activations=True)
+        rs = rs._replace(raw_activations=True, admm=admm)
         op, scl, rot = leaves["opacities"], leaves["scales"], leaves["rotations"]
     else:
         op = torch.sigmoid(leaves["opacities"])
@@ -134,19 +134,16 @@ def test_raw_activations_with_all_group_admm_fusion():
               "rotations": raw["rotations"].clone(), "opacities": raw["opacities"].clone()}
         for v in lv.values():
             v.requires_grad_(True)
-        plan = A.ConsensusPlan(torch.arange(P, device=DEV), torch.full((P,), 2, dtype=torch.int32, device=DEV))
-        blk = A.AdmmBlock([lv[k] for k in order], plan, alphas=(3e3, 2e3, 5e3, 1e3, 7e3, 9e2))
+        from test_gpu_aux_kernels import _virtual_plan
+        blk = A.AdmmBlock([lv[k] for k in order], _virtual_plan(P, A), alphas=(3e3, 2e3, 5e3, 1e3, 7e3, 9e2))
         gg = torch.Generator(device="cpu").manual_seed(5)
         for t in blk.zmu:
             t.add_(0.05 * torch.randn(t.shape, generator=gg).to(DEV))
         blk.fuse_into_rasterizer(fused, all_groups=fused)
-        try:
-            leaves = dict(lv, dc=lv["dc"].view(P, 1, 3), sh=lv["sh"].view(P, 15, 3))
-            img = _render(raw, fused, False, leaves)[0]
-            (img * w).sum().backward()
-            pens = blk.add_penalty_grads_().clone()
-        finally:
-            blk.fuse_into_rasterizer(False)
+        leaves = dict(lv, dc=lv["dc"].view(P, 1, 3), sh=lv["sh"].view(P, 15, 3))
+        img = _render(raw, fused, False, leaves, admm=blk)[0]
+        (img * w).sum().backward()
+        pens = blk.add_penalty_grads_().clone()
         torch.cuda.synchronize()
         return {k: v.grad.clone() for k, v in lv.items()}, pens
 

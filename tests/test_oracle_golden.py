@@ -146,3 +146,42 @@ def test_activations_golden():
     # numpy's float32 exp may differ from CUDA's expf in the last bit; the normalisation is exact arithmetic
     assert np.abs(o - g["opacity"]).max() <= 2e-7 and rel(s, g["scaling"]) <= 2e-7
     assert np.array_equal(q, g["quaternion"])
+
+
+def test_admm_oracle_matches_reference_methods_golden():
+    """oracle.admm_* (numpy restatement of master:326-456,538-555, slave:99-121,161-202 and
+    gaussian_splat_model.py:316-340) against tests/golden/admm.npz, produced by executing those reference
+    methods themselves (tools/make_golden_admm.py): z and u bit-exact, residuals / penalties to float32
+    reduction accuracy, the adapted rho identical."""
+    G = dict(np.load(os.path.join(GOLD, "admm.npz")))
+    K, n_global = int(G["K"]), int(G["n_global"])
+    names = ("xyz", "fdc", "fr", "s", "q", "o")
+    gidx = [G[f"global_indices_{k}"] for k in range(K)]
+    flat = lambda a: np.ascontiguousarray(a).reshape(a.shape[0], -1)
+    rho = list(G["rho_init"])
+    assert np.array_equal(np.array(rho), np.array([a / n_global for a in (1e5, 1e4, 1e5, 1e4, 1e5, 1e4)]))
+    z_prev = [flat(G[f"z0_{n}"]) for n in names]
+    u = [[np.zeros_like(flat(G[f"r0_x_{n}_{k}"])) for n in names] for k in range(K)]
+    z = z_prev
+    for rnd in range(3):
+        xs = [[flat(G[f"r{rnd}_x_{n}_{k}"]) for n in names] for k in range(K)]
+        if rnd > 0:
+            for k in range(K):
+                pens, grads = O.admm_penalty(xs[k], u[k], [zz[gidx[k]] for zz in z], rho)
+                assert np.allclose(pens, G[f"r{rnd}_penalty_{k}"], rtol=1e-5, atol=1e-12)
+                for gi, n in enumerate(names):
+                    assert rel(grads[gi], flat(G[f"r{rnd}_pengrad_{n}_{k}"])) <= 2e-6
+        z_prev = z
+        z, count = O.admm_consensus(xs, gidx, n_global)
+        assert np.array_equal(count.astype(np.int64), G["visibility_count"])
+        for gi, n in enumerate(names):
+            assert np.array_equal(bits(z[gi]), bits(flat(G[f"r{rnd}_z_{n}"]))), (rnd, n)
+        for k in range(K):
+            u[k] = O.admm_dual_update(xs[k], u[k], [zz[gidx[k]] for zz in z], 1.5)
+            for gi, n in enumerate(names):
+                assert np.array_equal(bits(u[k][gi]), bits(flat(G[f"r{rnd}_u_{n}_{k}"]))), (rnd, k, n)
+        primal, dual = O.admm_residuals(xs, gidx, z, z_prev, rho)
+        assert np.allclose(primal, G[f"r{rnd}_primal"], rtol=2e-6, atol=1e-14)
+        assert np.allclose(dual, G[f"r{rnd}_dual"], rtol=2e-6, atol=1e-14)
+        rho = O.admm_adapt(rho, primal, dual)
+        assert np.array_equal(np.array(rho), G[f"r{rnd}_rho_after"])
