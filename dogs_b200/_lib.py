@@ -62,8 +62,6 @@ SIGNATURES = {
                    + [C.POINTER(DgrForwardInfo), _P],
     "dgr_backward": [C.POINTER(DgrParams), C.c_int32] + [_P] * 8 + [_P] + [_P] * 3 + [_P, _P]
                     + [_P] * 9 + [ALLOC_FN, _P, _P],
-    "dgr_backward_timed": [C.POINTER(DgrParams), C.c_int32] + [_P] * 8 + [_P] + [_P] * 3 + [_P, _P]
-                          + [_P] * 9 + [ALLOC_FN, _P, _P, _P],
     "dgr_visible_filter": [C.POINTER(DgrParams), _P, _P, _P, _P, _P, _P],
     "dgr_mark_visible": [C.c_int32, _P, _P, _P, _P, _P],
     "dgr_apply_activations": [C.c_int32, _P, _P, _P, _P, _P, _P, _P],
@@ -86,6 +84,8 @@ SIGNATURES = {
     "dogs_last_error": [],
     "dogs_abi_version": [],
     "dogs_launch_count": [],
+    "dogs_stage_timing": [C.c_int],
+    "dogs_stage_times": [_P, C.c_int],
 }
 
 _lib = None
@@ -107,6 +107,7 @@ def lib():
         _lib.dogs_last_error.restype = C.c_char_p
         _lib.dogs_launch_count.restype = C.c_ulonglong
         _lib.admm_consensus_scratch_bytes.restype = C.c_size_t
+        _lib.dogs_stage_timing.restype = None
     return _lib
 
 

@@ -18,6 +18,12 @@ void set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
 
+// Optional per-stage device timing (dogs_stage_timing / dogs_stage_times): off by default; when on, the
+// instrumented entry points bracket their stages with CUDA events on the caller's stream and synchronise.
+static bool g_stage_timing = false;
+static float g_stage_ms[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+static int g_stage_n = 0;
+
 int check_launch(const char* what, bool debug, cudaStream_t s, int kernels) {
   g_launches += (unsigned long long)kernels;
   cudaError_t e = cudaGetLastError();
@@ -236,18 +242,19 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
   return 0;
 }
 
-static int backward_impl(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
+int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
                  const float* sh, const float* colors_precomp, const float* opacities,
                  const float* scales, const float* rotations, const float* cov3D_precomp,
                  const int32_t* radii, const char* geom, const char* binning, const char* image,
                  const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
                  float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
                  float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
-                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream, float* stage_ms) {
+                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (validate(prm)) return 1;
   const DgrParams& p = *prm;
   if (p.P == 0) return 0;
+  float* stage_ms = g_stage_timing ? g_stage_ms : nullptr;
   if (!geom || !binning || !image || !dL_dcolor) { set_error("backward: null state or gradient"); return 1; }
   if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacity) { set_error("backward: null output"); return 1; }
   if (!scratch_alloc) { set_error("backward: null scratch callback"); return 1; }
@@ -279,40 +286,20 @@ static int backward_impl(const DgrParams* prm, int32_t num_rendered, const float
     cudaEventSynchronize(ev[2]);
     cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
     cudaEventElapsedTime(&stage_ms[1], ev[1], ev[2]);
+    g_stage_n = 2;
     for (auto& e : ev) cudaEventDestroy(e);
   }
   return rc;
 }
 
-int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
-                 const float* sh, const float* colors_precomp, const float* opacities,
-                 const float* scales, const float* rotations, const float* cov3D_precomp,
-                 const int32_t* radii, const char* geom, const char* binning, const char* image,
-                 const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
-                 float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
-                 float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
-                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
-  return backward_impl(prm, num_rendered, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
-                       cov3D_precomp, radii, geom, binning, image, dL_dcolor, dL_dinvdepth_in, dL_dmeans3D,
-                       dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
-                       dL_drotations, dL_dcov3D, scratch_alloc, scratch_user, stream, nullptr);
-}
-
-// dgr_backward + device time of its two stages (CUDA events on `stream`; synchronises):
-// stage_ms[0] = accumulator clear + blend_bwd_kernel, stage_ms[1] = preprocess_bwd_kernel.
-int dgr_backward_timed(const DgrParams* prm, int32_t num_rendered, const float* means3D, const float* dc,
-                       const float* sh, const float* colors_precomp, const float* opacities,
-                       const float* scales, const float* rotations, const float* cov3D_precomp,
-                       const int32_t* radii, const char* geom, const char* binning, const char* image,
-                       const float* dL_dcolor, const float* dL_dinvdepth_in, float* dL_dmeans3D,
-                       float* dL_dmeans2D, float* dL_ddc, float* dL_dsh, float* dL_dcolors_precomp,
-                       float* dL_dopacity, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
-                       dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream, float* stage_ms) {
-  if (!stage_ms) { set_error("dgr_backward_timed: stage_ms is null"); return 1; }
-  return backward_impl(prm, num_rendered, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
-                       cov3D_precomp, radii, geom, binning, image, dL_dcolor, dL_dinvdepth_in, dL_dmeans3D,
-                       dL_dmeans2D, dL_ddc, dL_dsh, dL_dcolors_precomp, dL_dopacity, dL_dscales,
-                       dL_drotations, dL_dcov3D, scratch_alloc, scratch_user, stream, stage_ms);
+// Per-stage device timing for benchmarks (off by default).  While enabled, dgr_backward brackets its stages
+// with CUDA events on the caller's stream and synchronises; dogs_stage_times returns the last call's stage
+// times in ms: [0] accumulator clear + blend_bwd_kernel, [1] preprocess_bwd_kernel.
+void dogs_stage_timing(int enable) { g_stage_timing = enable != 0; g_stage_n = 0; }
+int dogs_stage_times(float* out_ms, int n) {
+  if (!out_ms || n > g_stage_n) { set_error("dogs_stage_times: %d stage(s) recorded", g_stage_n); return 1; }
+  for (int i = 0; i < n; i++) out_ms[i] = g_stage_ms[i];
+  return 0;
 }
 
 int dgr_apply_activations(int32_t P, const float* raw_opacities, const float* raw_scales,

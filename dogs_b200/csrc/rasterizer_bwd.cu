@@ -1,18 +1,15 @@
-// Backward rasterizer kernels (sm_100a).
+// Per-Gaussian backward of the rasterizer (sm_100a): preprocess_bwd_kernel fuses computeCov2DCUDA
+// (cuda_rasterizer/backward.cu:149-326) and preprocessCUDA (backward.cu:398-451) and writes every output
+// gradient exactly once (zeros for culled Gaussians), which removes the 308 B/Gaussian of torch::zeros
+// memsets (rasterize_points.cu:196-207).  It consumes the 12-float per-Gaussian accumulators written by
+// blend_bwd_kernel (blend_bwd.cu).
 //
-// blend_bwd_kernel replaces PerGaussianRenderCUDA (cuda_rasterizer/backward.cu:453-658).  The
-// reference walks each 32-splat bucket over the tile's 256 pixels and needs a (T, colour, depth)
-// snapshot per pixel per bucket from the forward pass (5 KB / bucket, ~2.7 GB at 3 M Gaussians).
-// Here every pixel thread replays its own front-to-back blend (T evolves exactly as in the
-// forward pass, the entry count is bounded by n_contrib), so no snapshot is stored at all.  The
-// 10 per-pair gradient terms are reduced across the warp with a transposed butterfly
-// (12 shuffles instead of 50), accumulated per tile in shared memory, and flushed with three
-// vector reductions (red.global.add.v4/v2.f32) per tile instance.
-//
-// preprocess_bwd_kernel fuses computeCov2DCUDA (backward.cu:149-326) and preprocessCUDA
-// (backward.cu:398-451) and writes every output gradient exactly once (zeros for culled
-// Gaussians), which removes the 308 B/Gaussian of torch::zeros memsets
-// (rasterize_points.cu:196-207).
+// Precision: the chain conic -> cov2D -> cov3D -> (scale, rotation) is evaluated in FP64.  For needle-shaped
+// Gaussians (axis ratios of 100 and more) it is ill-conditioned: the float32 evaluation — the reference's and
+// the first version of this kernel alike — is off by up to 1e-3 of the tensor maximum at 3 M Gaussians
+// against an FP64 evaluation of the same formulas (tools/gpu_truth_attrib.py: float32 accumulators + FP64
+// chain rule 1e-5, float32 chain rule 6e-4).  B200 issues FP64 at half the FP32 rate and the kernel is
+// HBM-bound, so the ~400 double operations per visible Gaussian hide behind the 520 B it moves.
 #include <string.h>
 #include "common.cuh"
 
@@ -21,57 +18,6 @@ namespace dogs {
 constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the global accumulator (3 x float4)
 // accumulator slots: 0 mean2D.x, 1 mean2D.y, 2 conic.x, 3 conic.y, 4 conic.w, 5 opacity,
 //                    6..8 colour rgb, 9 inverse depth, 10..11 unused
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
-__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
-
-// Sum 10 per-lane values over the warp.  After the call lane l holds the total of value
-// slot(l) (valid lanes only); every total lives in exactly two lanes (bit 0 of the lane id).
-__device__ __forceinline__ float warp_reduce10(const float v[10], int lane) {
-  const unsigned full = 0xffffffffu;
-  bool hi = lane & 16;
-  float k[5];
-#pragma unroll
-  for (int i = 0; i < 5; i++) {
-    float keep = hi ? v[5 + i] : v[i];
-    float send = hi ? v[i] : v[5 + i];
-    k[i] = keep + __shfl_xor_sync(full, send, 16);
-  }
-  hi = lane & 8;
-  float a0 = (hi ? k[3] : k[0]) + __shfl_xor_sync(full, hi ? k[0] : k[3], 8);
-  float a1 = (hi ? k[4] : k[1]) + __shfl_xor_sync(full, hi ? k[1] : k[4], 8);
-  float a2 = (hi ? 0.f : k[2]) + __shfl_xor_sync(full, hi ? k[2] : 0.f, 8);
-  hi = lane & 4;
-  float b0 = (hi ? a2 : a0) + __shfl_xor_sync(full, hi ? a0 : a2, 4);
-  float b1 = (hi ? 0.f : a1) + __shfl_xor_sync(full, hi ? a1 : 0.f, 4);
-  hi = lane & 2;
-  float c = (hi ? b1 : b0) + __shfl_xor_sync(full, hi ? b0 : b1, 2);
-  c += __shfl_xor_sync(full, c, 1);
-  return c;
-}
-// Which of the 10 values lane l ends up holding (-1: none / duplicate).
-__device__ __forceinline__ int warp_reduce10_slot(int lane) {
-  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
-  if (lane & 1) return -1;
-  const int i2 = 2 * b2 + b1;       // index among the 3 values of stage 3
-  if (i2 > 2) return -1;
-  const int i1 = 3 * b3 + i2;       // index among the 5 values of stage 2
-  if (b3 && i2 > 1) return -1;
-  return 5 * b4 + i1;
-}
 
 // ---- backward.cu:23-144 ---------------------------------------------------------------
 // sh_row: this Gaussian's staged SH "rest" row (3*M floats in shared memory); it is overwritten
@@ -152,6 +98,186 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, V3 pos, V3 campos, uin
   return r;
 }
 
+// ---- covariance chain: computeCov2DCUDA (backward.cu:165-325) + computeCov3D backward (:354-392) -------------
+// R3 = working precision.  In: the Gaussian (mean, activated scale * modifier, normalised quaternion or a
+// precomputed cov3D), the camera, and dL/dconic, dL/dopacity, dL/dinvdepth from the accumulators.
+// Out: the covariance-path part of dL/dmean3D, dL/dcov3D, dL/dscale, dL/drot, the (antialiasing-corrected)
+// dL/dopacity and the view-space depth.
+template <typename R3> struct Mat3 { R3 m[3][3]; };   // column-major m[c][r], GLM's product order
+template <typename R3>
+__device__ __forceinline__ Mat3<R3> mat3(R3 a, R3 b, R3 c, R3 d, R3 e, R3 f, R3 g, R3 h, R3 i) {
+  Mat3<R3> r;
+  r.m[0][0] = a; r.m[0][1] = b; r.m[0][2] = c;
+  r.m[1][0] = d; r.m[1][1] = e; r.m[1][2] = f;
+  r.m[2][0] = g; r.m[2][1] = h; r.m[2][2] = i;
+  return r;
+}
+template <typename R3> __device__ __forceinline__ Mat3<R3> mmul(const Mat3<R3>& A, const Mat3<R3>& B) {
+  Mat3<R3> C;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) C.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return C;
+}
+template <typename R3> __device__ __forceinline__ Mat3<R3> mtr(const Mat3<R3>& A) {
+  Mat3<R3> C;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) C.m[c][r] = A.m[r][c];
+  return C;
+}
+
+template <typename R3>
+__device__ __forceinline__ void cov_chain_bwd(const float3 mean_f, const float3 scale_f, const float4 rot_f,
+                                              float scale_modifier, const float* __restrict__ cov3D_pre,
+                                              const float* __restrict__ view, float h_x_f, float h_y_f,
+                                              float tan_fovx, float tan_fovy, bool antialiasing, float opac,
+                                              const float3 dL_dconic_f, float dL_dinvdepth_f, float& dL_dopac,
+                                              float3& g_mean3D, float g_cov3D[6], float g_scale[3], float4& g_rot,
+                                              float& depth_out) {
+  const R3 h_x = h_x_f, h_y = h_y_f;
+  const R3 half = R3(0.5), two = R3(2), one = R3(1);
+  R3 cov3D[6];
+  const R3 sx = R3(scale_modifier) * R3(scale_f.x), sy = R3(scale_modifier) * R3(scale_f.y), sz = R3(scale_modifier) * R3(scale_f.z);
+  // forward.cu:119-153 / backward.cu:330-352.  R and M = S * R are rebuilt where the cov3D backward needs them
+  // again instead of being kept alive across the cov2D part (18 doubles = 36 registers).
+  auto rotation = [&]() {
+    const R3 r = rot_f.x, x = rot_f.y, y = rot_f.z, z = rot_f.w;
+    return mat3<R3>(one - two * (y * y + z * z), two * (x * y - r * z), two * (x * z + r * y),
+                    two * (x * y + r * z), one - two * (x * x + z * z), two * (y * z - r * x),
+                    two * (x * z - r * y), two * (y * z + r * x), one - two * (x * x + y * y));
+  };
+  if (cov3D_pre != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) cov3D[i] = cov3D_pre[i];
+  } else {
+    const Mat3<R3> Mm = mmul(mat3<R3>(sx, 0, 0, 0, sy, 0, 0, 0, sz), rotation());
+    const Mat3<R3> Sigma = mmul(mtr(Mm), Mm);
+    cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
+  }
+  const R3 mx = mean_f.x, my = mean_f.y, mz = mean_f.z;
+  R3 tx = R3(view[0]) * mx + R3(view[4]) * my + R3(view[8]) * mz + R3(view[12]);
+  R3 ty = R3(view[1]) * mx + R3(view[5]) * my + R3(view[9]) * mz + R3(view[13]);
+  const R3 tz = R3(view[2]) * mx + R3(view[6]) * my + R3(view[10]) * mz + R3(view[14]);
+  depth_out = (float)tz;
+  const R3 limx = R3(1.3f) * R3(tan_fovx), limy = R3(1.3f) * R3(tan_fovy);
+  const R3 txtz = tx / tz, tytz = ty / tz;
+  tx = min(limx, max(-limx, txtz)) * tz;
+  ty = min(limy, max(-limy, tytz)) * tz;
+  const R3 x_grad_mul = (txtz < -limx || txtz > limx) ? R3(0) : one;
+  const R3 y_grad_mul = (tytz < -limy || tytz > limy) ? R3(0) : one;
+  const Mat3<R3> J = mat3<R3>(h_x / tz, 0, -(h_x * tx) / (tz * tz), 0, h_y / tz, -(h_y * ty) / (tz * tz), 0, 0, 0);
+  const Mat3<R3> Wm = mat3<R3>(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
+  const Mat3<R3> Vrk = mat3<R3>(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+  const Mat3<R3> Tm = mmul(Wm, J);
+  const Mat3<R3> cov2D = mmul(mmul(mtr(Tm), mtr(Vrk)), Tm);
+  R3 c_xx = cov2D.m[0][0], c_xy = cov2D.m[0][1], c_yy = cov2D.m[1][1];
+  const R3 h_var = R3(0.3f);
+  R3 d_inside_root = 0;
+  if (antialiasing) {
+    const R3 det_cov = c_xx * c_yy - c_xy * c_xy;
+    c_xx += h_var;
+    c_yy += h_var;
+    const R3 det_cov_plus_h_cov = c_xx * c_yy - c_xy * c_xy;
+    const R3 h_convolution_scaling = sqrt(max(R3(0.000025f), det_cov / det_cov_plus_h_cov));
+    const R3 dL_dopacity_v = dL_dopac;
+    const R3 d_h_convolution_scaling = dL_dopacity_v * R3(opac);
+    dL_dopac = (float)(dL_dopacity_v * h_convolution_scaling);
+    d_inside_root = (det_cov / det_cov_plus_h_cov) <= R3(0.000025f) ? R3(0)
+                                                                   : d_h_convolution_scaling / (two * h_convolution_scaling);
+  } else {
+    c_xx += h_var;
+    c_yy += h_var;
+  }
+  R3 dL_dc_xx = 0, dL_dc_xy = 0, dL_dc_yy = 0;
+  if (antialiasing) {
+    const R3 x = c_xx, y = c_yy, z = c_xy, w = h_var;
+    const R3 q = w * w + w * (x + y) + x * y - z * z;
+    const R3 denom_f = d_inside_root / (q * q);
+    dL_dc_xx = w * (w * y + y * y + z * z) * denom_f;
+    dL_dc_yy = w * (w * x + x * x + z * z) * denom_f;
+    dL_dc_xy = -two * w * z * (w + x + y) * denom_f;
+  }
+  const R3 dcx = dL_dconic_f.x, dcy = dL_dconic_f.y, dcz = dL_dconic_f.z;
+  const R3 denom = c_xx * c_yy - c_xy * c_xy;
+  const R3 denom2inv = one / ((denom * denom) + R3(0.0000001f));
+  R3 gc[6] = {0, 0, 0, 0, 0, 0};
+  if (denom2inv != 0) {
+    dL_dc_xx += denom2inv * (-c_yy * c_yy * dcx + two * c_xy * c_yy * dcy + (denom - c_xx * c_yy) * dcz);
+    dL_dc_yy += denom2inv * (-c_xx * c_xx * dcz + two * c_xx * c_xy * dcy + (denom - c_xx * c_yy) * dcx);
+    dL_dc_xy += denom2inv * two * (c_xy * c_yy * dcx - (denom + two * c_xy * c_xy) * dcy + c_xx * c_xy * dcz);
+    const R3 T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
+    const R3 T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
+    gc[0] = (T00 * T00 * dL_dc_xx + T00 * T10 * dL_dc_xy + T10 * T10 * dL_dc_yy);
+    gc[3] = (T01 * T01 * dL_dc_xx + T01 * T11 * dL_dc_xy + T11 * T11 * dL_dc_yy);
+    gc[5] = (T02 * T02 * dL_dc_xx + T02 * T12 * dL_dc_xy + T12 * T12 * dL_dc_yy);
+    gc[1] = two * T00 * T01 * dL_dc_xx + (T00 * T11 + T01 * T10) * dL_dc_xy + two * T10 * T11 * dL_dc_yy;
+    gc[2] = two * T00 * T02 * dL_dc_xx + (T00 * T12 + T02 * T10) * dL_dc_xy + two * T10 * T12 * dL_dc_yy;
+    gc[4] = two * T02 * T01 * dL_dc_xx + (T01 * T12 + T02 * T11) * dL_dc_xy + two * T11 * T12 * dL_dc_yy;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) g_cov3D[i] = (float)gc[i];
+  R3 dL_dT[2][3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const R3 a = Tm.m[0][0] * Vrk.m[k][0] + Tm.m[0][1] * Vrk.m[k][1] + Tm.m[0][2] * Vrk.m[k][2];
+    const R3 b = Tm.m[1][0] * Vrk.m[k][0] + Tm.m[1][1] * Vrk.m[k][1] + Tm.m[1][2] * Vrk.m[k][2];
+    dL_dT[0][k] = two * a * dL_dc_xx + b * dL_dc_xy;
+    dL_dT[1][k] = two * b * dL_dc_yy + a * dL_dc_xy;
+  }
+  const R3 dL_dJ00 = Wm.m[0][0] * dL_dT[0][0] + Wm.m[0][1] * dL_dT[0][1] + Wm.m[0][2] * dL_dT[0][2];
+  const R3 dL_dJ02 = Wm.m[2][0] * dL_dT[0][0] + Wm.m[2][1] * dL_dT[0][1] + Wm.m[2][2] * dL_dT[0][2];
+  const R3 dL_dJ11 = Wm.m[1][0] * dL_dT[1][0] + Wm.m[1][1] * dL_dT[1][1] + Wm.m[1][2] * dL_dT[1][2];
+  const R3 dL_dJ12 = Wm.m[2][0] * dL_dT[1][0] + Wm.m[2][1] * dL_dT[1][1] + Wm.m[2][2] * dL_dT[1][2];
+  const R3 itz = one / tz;
+  const R3 tz2 = itz * itz;
+  const R3 tz3 = tz2 * itz;
+  const R3 dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+  const R3 dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+  const R3 dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (two * h_x * tx) * tz3 * dL_dJ02 +
+                    (two * h_y * ty) * tz3 * dL_dJ12 - R3(dL_dinvdepth_f) * tz2;
+  // transformVec4x3Transpose (auxiliary.h:100-108)
+  g_mean3D = {(float)(R3(view[0]) * dL_dtx + R3(view[1]) * dL_dty + R3(view[2]) * dL_dtz),
+              (float)(R3(view[4]) * dL_dtx + R3(view[5]) * dL_dty + R3(view[6]) * dL_dtz),
+              (float)(R3(view[8]) * dL_dtx + R3(view[9]) * dL_dty + R3(view[10]) * dL_dtz)};
+  if (cov3D_pre == nullptr) {
+    // computeCov3D backward (backward.cu:354-392).  The scale gradient is dot(Rt[i], dL_dMt[i]), not
+    // multiplied by the modifier, as in the reference (backward.cu:374-377).
+    const Mat3<R3> dL_dSigma = mat3<R3>(gc[0], half * gc[1], half * gc[2], half * gc[1], gc[3], half * gc[4],
+                                        half * gc[2], half * gc[4], gc[5]);
+    const Mat3<R3> Rm = rotation();
+    const Mat3<R3> Mm = mmul(mat3<R3>(sx, 0, 0, 0, sy, 0, 0, 0, sz), Rm);
+    Mat3<R3> dL_dM = mmul(Mm, dL_dSigma);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) dL_dM.m[c][r] *= two;
+    const Mat3<R3> Rt = mtr(Rm);
+    Mat3<R3> dMt = mtr(dL_dM);
+    g_scale[0] = (float)(Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2]);
+    g_scale[1] = (float)(Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2]);
+    g_scale[2] = (float)(Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2]);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      dMt.m[0][r] *= sx;
+      dMt.m[1][r] *= sy;
+      dMt.m[2][r] *= sz;
+    }
+    const R3 r = rot_f.x, x = rot_f.y, y = rot_f.z, z = rot_f.w;
+    const R3 four = R3(4);
+    g_rot.x = (float)(two * z * (dMt.m[0][1] - dMt.m[1][0]) + two * y * (dMt.m[2][0] - dMt.m[0][2]) + two * x * (dMt.m[1][2] - dMt.m[2][1]));
+    g_rot.y = (float)(two * y * (dMt.m[1][0] + dMt.m[0][1]) + two * z * (dMt.m[2][0] + dMt.m[0][2]) + two * r * (dMt.m[1][2] - dMt.m[2][1]) - four * x * (dMt.m[2][2] + dMt.m[1][1]));
+    g_rot.z = (float)(two * x * (dMt.m[1][0] + dMt.m[0][1]) + two * r * (dMt.m[2][0] - dMt.m[0][2]) + two * z * (dMt.m[1][2] + dMt.m[2][1]) - four * y * (dMt.m[2][2] + dMt.m[0][0]));
+    g_rot.w = (float)(two * r * (dMt.m[0][1] - dMt.m[1][0]) + two * x * (dMt.m[2][0] + dMt.m[0][2]) + two * y * (dMt.m[1][2] + dMt.m[2][1]) - four * z * (dMt.m[1][1] + dMt.m[0][0]));
+  }
+}
+
+#ifndef DOGS_PREB_REAL
+#define DOGS_PREB_REAL double
+#endif
 constexpr int PREB_THREADS = 128;
 
 __global__ void __launch_bounds__(PREB_THREADS, 5)
@@ -220,117 +346,15 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       float3 scale = {0.f, 0.f, 0.f};
       float4 rot = {0.f, 0.f, 0.f, 0.f}, raw_rot = {0.f, 0.f, 0.f, 0.f};
       const float opac = raw_inputs ? act_sigmoid(opacities[idx]) : opacities[idx];
-      float cov3D[6];
-      M3 R, Mm;
-      float3 s = {0.f, 0.f, 0.f};
-      if (cov3D_precomp != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) cov3D[i] = cov3D_precomp[6 * idx + i];
-      } else {
+      if (cov3D_precomp == nullptr) {
         scale = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
         rot = reinterpret_cast<const float4*>(rotations)[idx];
         if (raw_inputs) { raw_rot = rot; scale = act_exp3(scale); rot = act_normalize(rot); }
-        // forward.cu:119-153 / backward.cu:330-352
-        const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-        R = m3(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-               2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-               2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-        s = {scale_modifier * scale.x, scale_modifier * scale.y, scale_modifier * scale.z};
-        M3 S = m3(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
-        Mm = S * R;
-        M3 Sigma = transpose(Mm) * Mm;
-        cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
-        cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
       }
-
-      // ---- computeCov2DCUDA (backward.cu:165-325) ----
-      float3 t = xform4x3(mean, view);
-      const float depth = t.z;
-      const float limx = 1.3f * tan_fovx;
-      const float limy = 1.3f * tan_fovy;
-      const float txtz = t.x / t.z;
-      const float tytz = t.y / t.z;
-      t.x = min(limx, max(-limx, txtz)) * t.z;
-      t.y = min(limy, max(-limy, tytz)) * t.z;
-      const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
-      const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
-      M3 J = m3(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z,
-                -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
-      M3 Wm = m3(view[0], view[4], view[8], view[1], view[5], view[9], view[2], view[6], view[10]);
-      M3 Vrk = m3(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4],
-                  cov3D[5]);
-      M3 Tm = Wm * J;
-      M3 cov2D = transpose(Tm) * transpose(Vrk) * Tm;
-      float c_xx = cov2D.m[0][0], c_xy = cov2D.m[0][1], c_yy = cov2D.m[1][1];
-      constexpr float h_var = 0.3f;
-      float d_inside_root = 0.f;
-      if (antialiasing) {
-        const float det_cov = c_xx * c_yy - c_xy * c_xy;
-        c_xx += h_var;
-        c_yy += h_var;
-        const float det_cov_plus_h_cov = c_xx * c_yy - c_xy * c_xy;
-        const float h_convolution_scaling = sqrt(max(0.000025f, det_cov / det_cov_plus_h_cov));
-        const float dL_dopacity_v = dL_dopac;
-        const float d_h_convolution_scaling = dL_dopacity_v * opac;
-        dL_dopac = dL_dopacity_v * h_convolution_scaling;
-        d_inside_root = (det_cov / det_cov_plus_h_cov) <= 0.000025f
-                            ? 0.f
-                            : d_h_convolution_scaling / (2 * h_convolution_scaling);
-      } else {
-        c_xx += h_var;
-        c_yy += h_var;
-      }
-      float dL_dc_xx = 0, dL_dc_xy = 0, dL_dc_yy = 0;
-      if (antialiasing) {
-        const float x = c_xx, y = c_yy, z = c_xy, w = h_var;
-        const float q = w * w + w * (x + y) + x * y - z * z;
-        const float denom_f = d_inside_root / (q * q);
-        dL_dc_xx = w * (w * y + y * y + z * z) * denom_f;
-        dL_dc_yy = w * (w * x + x * x + z * z) * denom_f;
-        dL_dc_xy = -2.f * w * z * (w + x + y) * denom_f;
-      }
-      const float denom = c_xx * c_yy - c_xy * c_xy;
-      const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-      if (denom2inv != 0) {
-        dL_dc_xx += denom2inv * (-c_yy * c_yy * dL_dconic.x + 2 * c_xy * c_yy * dL_dconic.y +
-                                 (denom - c_xx * c_yy) * dL_dconic.z);
-        dL_dc_yy += denom2inv * (-c_xx * c_xx * dL_dconic.z + 2 * c_xx * c_xy * dL_dconic.y +
-                                 (denom - c_xx * c_yy) * dL_dconic.x);
-        dL_dc_xy += denom2inv * 2 * (c_xy * c_yy * dL_dconic.x -
-                                     (denom + 2 * c_xy * c_xy) * dL_dconic.y +
-                                     c_xx * c_xy * dL_dconic.z);
-        const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
-        const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
-        g_cov3D[0] = (T00 * T00 * dL_dc_xx + T00 * T10 * dL_dc_xy + T10 * T10 * dL_dc_yy);
-        g_cov3D[3] = (T01 * T01 * dL_dc_xx + T01 * T11 * dL_dc_xy + T11 * T11 * dL_dc_yy);
-        g_cov3D[5] = (T02 * T02 * dL_dc_xx + T02 * T12 * dL_dc_xy + T12 * T12 * dL_dc_yy);
-        g_cov3D[1] = 2 * T00 * T01 * dL_dc_xx + (T00 * T11 + T01 * T10) * dL_dc_xy + 2 * T10 * T11 * dL_dc_yy;
-        g_cov3D[2] = 2 * T00 * T02 * dL_dc_xx + (T00 * T12 + T02 * T10) * dL_dc_xy + 2 * T10 * T12 * dL_dc_yy;
-        g_cov3D[4] = 2 * T02 * T01 * dL_dc_xx + (T01 * T12 + T02 * T11) * dL_dc_xy + 2 * T11 * T12 * dL_dc_yy;
-      }
-      float dL_dT[2][3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const float a = Tm.m[0][0] * Vrk.m[k][0] + Tm.m[0][1] * Vrk.m[k][1] + Tm.m[0][2] * Vrk.m[k][2];
-        const float b = Tm.m[1][0] * Vrk.m[k][0] + Tm.m[1][1] * Vrk.m[k][1] + Tm.m[1][2] * Vrk.m[k][2];
-        dL_dT[0][k] = 2 * a * dL_dc_xx + b * dL_dc_xy;
-        dL_dT[1][k] = 2 * b * dL_dc_yy + a * dL_dc_xy;
-      }
-      const float dL_dJ00 = Wm.m[0][0] * dL_dT[0][0] + Wm.m[0][1] * dL_dT[0][1] + Wm.m[0][2] * dL_dT[0][2];
-      const float dL_dJ02 = Wm.m[2][0] * dL_dT[0][0] + Wm.m[2][1] * dL_dT[0][1] + Wm.m[2][2] * dL_dT[0][2];
-      const float dL_dJ11 = Wm.m[1][0] * dL_dT[1][0] + Wm.m[1][1] * dL_dT[1][1] + Wm.m[1][2] * dL_dT[1][2];
-      const float dL_dJ12 = Wm.m[2][0] * dL_dT[1][0] + Wm.m[2][1] * dL_dT[1][1] + Wm.m[2][2] * dL_dT[1][2];
-      const float tz = 1.f / t.z;
-      const float tz2 = tz * tz;
-      const float tz3 = tz2 * tz;
-      const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-      const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-      const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
-                           (2 * h_y * t.y) * tz3 * dL_dJ12 - dL_dinvdepth * tz2;
-      // transformVec4x3Transpose (auxiliary.h:100-108)
-      g_mean3D = {view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz,
-                  view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz,
-                  view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz};
+      float depth;
+      cov_chain_bwd<DOGS_PREB_REAL>(mean, scale, rot, scale_modifier, cov3D_precomp ? cov3D_precomp + 6 * idx : nullptr,
+                                    view, h_x, h_y, tan_fovx, tan_fovy, antialiasing, opac, dL_dconic, dL_dinvdepth,
+                                    dL_dopac, g_mean3D, g_cov3D, g_scale, g_rot, depth);
 
       // ---- preprocessCUDA backward (backward.cu:421-450) ----
       float4 m_hom = xform4x4(mean, proj);
@@ -349,35 +373,6 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         g_mean3D.x += dm.x; g_mean3D.y += dm.y; g_mean3D.z += dm.z;
       }
 
-      if (cov3D_precomp == nullptr) {
-        // computeCov3D backward (backward.cu:354-392)
-        M3 dL_dSigma = m3(g_cov3D[0], 0.5f * g_cov3D[1], 0.5f * g_cov3D[2], 0.5f * g_cov3D[1],
-                          g_cov3D[3], 0.5f * g_cov3D[4], 0.5f * g_cov3D[2], 0.5f * g_cov3D[4],
-                          g_cov3D[5]);
-        M3 dL_dM = Mm * dL_dSigma;
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-          for (int r = 0; r < 3; r++) dL_dM.m[c][r] *= 2.0f;
-        M3 Rt = transpose(R);
-        M3 dL_dMt = transpose(dL_dM);
-        g_scale[0] = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
-        g_scale[1] = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
-        g_scale[2] = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-          dL_dMt.m[0][r] *= s.x;
-          dL_dMt.m[1][r] *= s.y;
-          dL_dMt.m[2][r] *= s.z;
-        }
-        const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-        g_rot.x = 2 * z * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * y * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * x * (dL_dMt.m[1][2] - dL_dMt.m[2][1]);
-        g_rot.y = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
-        g_rot.z = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
-        g_rot.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
-        // scale gradient is w.r.t. the given scale: dL/dscale = mod * dL/d(mod*scale)?  No — the
-        // reference returns dot(Rt[i], dL_dMt[i]) unscaled by mod (backward.cu:374-377); keep it.
-      }
       g_opacity = dL_dopac;
       if (raw_inputs) {
         // chain rule through the activations, in the form of torch's own backward formulas

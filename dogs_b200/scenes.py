@@ -131,3 +131,53 @@ def render(mod, scene, params=None, **kw):
                                      shs=p["sh"], colors_precomp=None, opacities=p["opacities"],
                                      scales=p["scales"], rotations=p["rotations"], cov3D_precomp=None)
     return image, radii, depth, screen_space_points
+
+
+# ---- ADMM block scenes (BASELINE.json configs 4 and 5) -------------------------------------
+# A 4 x 2 grid of unit cells in xy; block b owns its cell expanded x1.4 about its centre
+# (config/gaussian_splatting/urban3d_admm.yaml:18-20), so neighbouring blocks overlap by 0.4 and corner
+# Gaussians have up to four owners.  The global cloud is uniform over the union of the expanded cells, which
+# gives every block the same expected size; block b's camera hovers over its cell centre (nadir, height 3).
+ADMM_SPECS = {"C4": dict(per_block=2_000_000, grid=(4, 2)), "C5": dict(per_block=4_000_000, grid=(4, 2))}
+ADMM_EXPAND = 1.4
+ADMM_DEPTH_THRESHOLD = 0.23             # urban3d_admm.yaml:86
+
+
+def admm_layout(cfg, seed=0, per_block=None):
+    """(xyz float32 [n_global, 3] on CPU, [global_indices int64 per block], boxes float64 [n_blocks, 2, 3])."""
+    spec = ADMM_SPECS[cfg]
+    gx, gy = spec["grid"]
+    per_block = spec["per_block"] if per_block is None else per_block
+    m = 0.5 * (ADMM_EXPAND - 1.0)
+    n_global = int(round(per_block / (ADMM_EXPAND * ADMM_EXPAND) * (gx + 2 * m) * (gy + 2 * m)))
+    g = torch.Generator(device="cpu").manual_seed(1000 + seed)
+    xy = torch.rand(n_global, 2, generator=g, dtype=torch.float32)
+    xyz = torch.stack([xy[:, 0] * (gx + 2 * m) - m, xy[:, 1] * (gy + 2 * m) - m,
+                       torch.randn(n_global, generator=g, dtype=torch.float32) * 0.1], dim=1).contiguous()
+    boxes, gidx = [], []
+    h = 0.5 * ADMM_EXPAND
+    for by in range(gy):
+        for bx in range(gx):
+            cx, cy = bx + 0.5, by + 0.5
+            boxes.append([[cx - h, cy - h, -10.0], [cx + h, cy + h, 10.0]])
+            inside = (xyz[:, 0] >= cx - h) & (xyz[:, 0] <= cx + h) & (xyz[:, 1] >= cy - h) & (xyz[:, 1] <= cy + h)
+            gidx.append(torch.nonzero(inside).squeeze(1))
+    return xyz, gidx, torch.tensor(boxes, dtype=torch.float64)
+
+
+def make_admm_block(cfg, block, xyz_block, seed=0, device="cpu", W=1920, H=1080, fx=1500.0, sh_degree=3):
+    """Scene dict of one block with RAW consensus parameters (pre-activation opacity / scaling / quaternion, the
+    ADMM variables of slave_gaussian_trainer.py:81-97), distributions as C3."""
+    gx, _ = ADMM_SPECS[cfg]["grid"]
+    P = xyz_block.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(7919 * (seed + 1) + block)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32)
+    out = dict(means3D=xyz_block.contiguous(), dc=rn(P, 1, 3), sh=rn(P, 15, 3) * 0.1,
+               opacities=rn(P, 1) * 1.5, scales=rn(P, 3) * 0.7 + math.log(0.006), rotations=rn(P, 4),
+               sh_degree=sh_degree, name=f"{cfg}/block{block}")
+    w2c = torch.eye(4)
+    w2c[0, 3], w2c[1, 3], w2c[2, 3] = -((block % gx) + 0.5), -((block // gx) + 0.5), 3.0
+    out.update(make_camera(W, H, fx, fx, w2c))
+    if device != "cpu":
+        out = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+    return out

@@ -126,21 +126,6 @@ int dgr_backward(const DgrParams* prm, int32_t num_rendered,
                  float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                  dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
 
-/* dgr_backward + the device time (ms, CUDA events on `stream`; synchronises) of its two stages:
- * stage_ms[0] = accumulator clear + blend_bwd_kernel, stage_ms[1] = preprocess_bwd_kernel.
- * Used by bench.py for the per-kernel roofline. */
-int dgr_backward_timed(const DgrParams* prm, int32_t num_rendered,
-                 const float* means3D, const float* dc, const float* sh,
-                 const float* colors_precomp, const float* opacities,
-                 const float* scales, const float* rotations, const float* cov3D_precomp,
-                 const int32_t* radii,
-                 const char* geom, const char* binning, const char* image,
-                 const float* dL_dcolor, const float* dL_dinvdepth_in,
-                 float* dL_dmeans3D, float* dL_dmeans2D, float* dL_ddc, float* dL_dsh,
-                 float* dL_dcolors_precomp, float* dL_dopacity,
-                 float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
-                 dogs_alloc_fn scratch_alloc, void* scratch_user, void* stream, float* stage_ms);
-
 /* rasterize_gaussians_filter (rasterize_points.cu:274-329): radii only, no +0.3 low-pass. */
 int dgr_visible_filter(const DgrParams* prm, const float* means3D, const float* scales,
                        const float* rotations, const float* cov3D_precomp,
@@ -275,6 +260,11 @@ const char* dogs_last_error(void);
 int dogs_abi_version(void);
 /* Number of kernels this library has launched so far in the process (bench.py reports the delta). */
 unsigned long long dogs_launch_count(void);
+/* Benchmark hook, off by default: while enabled, dgr_backward brackets its stages with CUDA events on the
+ * caller's stream and synchronises; dogs_stage_times copies the last call's stage times (ms) to out_ms:
+ * [0] accumulator clear + blend_bwd_kernel, [1] preprocess_bwd_kernel. */
+void dogs_stage_timing(int enable);
+int dogs_stage_times(float* out_ms, int n);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,22 @@ def build(force=False):
     return LIB
 
 
+TRUTH_LIB = os.path.join(HERE, "libtruth.so")
+
+
+def build_truth(force=False):
+    """FP64 truth of the rasterizer backward (oracle/truth_bwd.cu, CUDA, test infrastructure): cross-compiled
+    for sm_100a where nvcc exists; the GPU box uses the prebuilt file."""
+    src = os.path.join(HERE, "truth_bwd.cu")
+    if force or not os.path.exists(TRUTH_LIB) or os.path.getmtime(TRUTH_LIB) < os.path.getmtime(src):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if not os.path.exists(nvcc):
+            return None
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-shared",
+                               "-Xcompiler", "-fPIC", "-o", TRUTH_LIB, src, "-lcudart"])
+    return TRUTH_LIB
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -194,8 +194,55 @@ def ours_forward_raw(scene, bg=None, antialiasing=False, depth_threshold=0.0, de
                ranges=im[lay.img_ranges:lay.img_ranges + 8 * T].view(torch.int32).view(T, 2),
                final_T=im[lay.img_final_T:lay.img_final_T + 4 * N].view(torch.float32),
                n_contrib=im[lay.img_n_contrib:lay.img_n_contrib + 4 * N].view(torch.int32),
-               _keep=(al, keep))
+               _keep=(al, keep), _bg=bg, _rec=g[lay.geom_record:lay.geom_record + 48 * P])
     return out
+
+
+_truth = None
+
+
+def truth_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "libtruth.so"))
+
+
+def truth_backward(scene, o, dL_dcolor, dL_dinvdepth, depth_threshold=0.0):
+    """FP64 evaluation of the reference's backward formulas (oracle/truth_bwd.cu, test infrastructure) on the
+    float32 forward state `o` = ours_forward_raw(scene), which is bit-identical to the reference's.  Returns
+    float64 gradients keyed like GRAD_KEYS; no antialiasing, scale/rotation inputs, SH colours."""
+    global _truth
+    if _truth is None:
+        _truth = C.CDLL(os.path.join(ROOT, "oracle", "libtruth.so"))
+    dev = scene["means3D"].device
+    P, H, W = scene["means3D"].shape[0], int(scene["H"]), int(scene["W"])
+    M, D = scene["sh"].shape[1], int(scene["sh_degree"])
+    acc = torch.zeros(P, 10, dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    dLc = dL_dcolor.contiguous()
+    dLd = dL_dinvdepth.contiguous() if dL_dinvdepth is not None else None
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = _truth.truth_blend_bwd(C.c_int(W), C.c_int(H), p(o["ranges"]), p(o["point_list"]), p(o["_bg"]), p(o["_rec"]),
+                                p(o["n_contrib"]), p(dLc), p(dLd), p(acc), st)
+    assert rc == 0, f"truth_blend_bwd: CUDA error {rc}"
+    new = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+    g3, g2, gdc, gsh, gop, gsc, grot = new(P, 3), new(P, 2), new(P, 3), new(P, M, 3), new(P), new(P, 3), new(P, 4)
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))      # the forward consumed float32 values
+    rc = _truth.truth_preprocess_bwd(
+        C.c_int(P), C.c_int(D), C.c_int(M), C.c_int(W), C.c_int(H), p(scene["means3D"]), p(o["radii"]), p(scene["sh"]),
+        p(o["clamped"]), p(scene["scales"]), p(scene["rotations"]), C.c_double(1.0), p(scene["viewmatrix"]),
+        p(scene["projmatrix"]), C.c_double(f32(scene["tanfovx"])), C.c_double(f32(scene["tanfovy"])), p(scene["campos"]),
+        p(acc), C.c_double(depth_threshold), p(g3), p(g2), p(gdc), p(gsh), p(gop), p(gsc), p(grot), st)
+    assert rc == 0, f"truth_preprocess_bwd: CUDA error {rc}"
+    torch.cuda.synchronize()
+    m2 = torch.zeros(P, 3, dtype=torch.float64, device=dev)
+    m2[:, :2] = g2
+    return {"means3D": g3, "means2D": m2, "dc": gdc.view(P, 1, 3), "sh": gsh, "opacities": gop.view(P, 1),
+            "scales": gsc, "rotations": grot}
+
+
+def err_vs_truth(a, truth):
+    """max |a - truth| / max |truth| with the comparison done in float64."""
+    t = truth.reshape(a.shape)
+    return float((a.double() - t).abs().max() / t.abs().max().clamp_min(1e-300))
 
 
 def bits(t):

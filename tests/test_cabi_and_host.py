@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "dogs_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+char\s*\*|unsigned\s+long\s+long|size_t|int)\s+(\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+char\s*\*|unsigned\s+long\s+long|size_t|void|int)\s+(\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 

@@ -119,7 +119,7 @@ def _virtual_plan(P, A):
     plan = A.BlockPlan(0, P, P)
     plan.shared_row = torch.arange(P, dtype=torch.int32, device=DEV)
     plan.S, plan.max_addends = P, 1
-    plan.addends = torch.full((P, 1), A.SELF_ADDEND, dtype=torch.int32, device=DEV)
+    plan.addends = torch.full((P, 1), A.SELF_ADDEND - (1 << 32), dtype=torch.int32, device=DEV)   # uint32 bit pattern
     plan.count = torch.ones(P, dtype=torch.uint8, device=DEV)
     plan.pack_src = torch.zeros(0, dtype=torch.int32, device=DEV)
     topo = A.Topology()

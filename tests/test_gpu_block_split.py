@@ -43,9 +43,13 @@ def test_select_gaussians_in_each_block_vs_oracle(n, use_obb):
         assert np.array_equal(a.cpu().numpy(), b)
     if n > 1000:
         assert int((vis > 1).sum()) > 0 and valid.numel() < n      # overlaps and outliers both present
-    # the indices feed the consensus plan directly
-    plan = A.ConsensusPlan(gidx[0], vis.to(torch.int32))
-    assert plan.n_local == gidx[0].numel() and plan.S == int((vis[gidx[0]] > 1).sum())
+    # the indices feed the consensus topology directly
+    if all(g.numel() for g in gidx):
+        topo = A.build_topology({b: g for b, g in enumerate(gidx)}, int(valid.numel()))
+        for b, g in enumerate(gidx):
+            plan = topo.plans[b]
+            assert plan.n_local == g.numel() and plan.S == int((vis[g] > 1).sum())
+            assert torch.equal(plan.count.long(), vis[g][vis[g] > 1])
 
 
 def test_fuse_block_gaussians_drops_points_outside_own_box():

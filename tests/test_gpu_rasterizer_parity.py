@@ -108,6 +108,31 @@ def test_backward_matches_reference(case, mode):
         assert U.rel_to_max(a, b) <= GRAD_TOL, (k, U.rel_to_max(a, b))
 
 
+def test_backward_vs_fp64_truth(case):
+    """The FP64 evaluation of the reference's backward formulas (oracle/truth_bwd.cu) on the shared forward
+    state: at these sizes both float32 backwards sit well inside the 1e-4 bar around it, which validates the
+    truth that adjudicates the full-size test below."""
+    if case["aa"] or not U.truth_available():
+        pytest.skip("truth covers antialiasing=False / libtruth.so not built")
+    sc, r, dgr, o = case["sc"], case["ref"], case["dgr"], case["ours"]
+    H, W = sc["H"], sc["W"]
+    ri = U.parse_ref_image(r["img"], H * W)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    saved = ri["max_contrib"][:T].clone()
+    ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
+    dLc, dLd = _out_grads(sc)
+    try:
+        gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+        torch.cuda.synchronize()
+    finally:
+        ri["max_contrib"][:T] = saved
+    truth = U.truth_backward(sc, o, dLc, dLd)
+    go = U.ours_backward(sc, dLc, dLd)
+    for k in GRAD_KEYS:
+        assert U.err_vs_truth(go[k], truth[k]) <= 0.5 * GRAD_TOL, (k, U.err_vs_truth(go[k], truth[k]))
+        assert U.err_vs_truth(gr[k].reshape(go[k].shape), truth[k]) <= 0.5 * GRAD_TOL, k
+
+
 def test_forward_and_backward_vs_cpu_oracle():
     """Same seeded inputs through the CPU restatement (tiny scene: the oracle finishes in < 1 s)."""
     from oracle import oracle as O
@@ -352,28 +377,28 @@ def test_full_size_properties(cfg):
         T = ((W + 15) // 16) * ((H + 15) // 16)
         ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
         dLc, dLd = _out_grads(sc)
-        # The reference accumulates with float atomics in scheduling order, so at 3 M Gaussians its own
-        # gradients move from run to run (tools/gpu_grad_noise.py on C3: rotations 1.8e-4, scales 4.9e-5
-        # of max|g| between two runs, everything else <= 1.3e-6): a handful of ill-conditioned
-        # Gaussians out of 3 M exceed GRAD_TOL in the reference against itself (1-2 elements of 12 M for
-        # rotations; this package against the reference: ~10, its own atomics add their share).  The
-        # full-size bar is therefore statistical: at most 1 element in 10^5 beyond GRAD_TOL (or 3x the
-        # reference's own count if that is larger) and none beyond 10x GRAD_TOL.  tiny/C1 keep the plain bar.
-        runs = []
-        for _ in range(3):
-            gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
-            runs.append({k: gr[k].clone() for k in GRAD_KEYS})
-        gr = runs[0]
-        ref_out = {k: max(U.count_outliers(runs[1][k], gr[k], GRAD_TOL), U.count_outliers(runs[2][k], gr[k], GRAD_TOL),
-                          U.count_outliers(runs[2][k], runs[1][k], GRAD_TOL)) for k in GRAD_KEYS}
-        del r, ri, rb, runs
-        del o, o2
+        # Adjudicated by an FP64 evaluation of the reference's own backward formulas on the same (bit-identical)
+        # forward state (oracle/truth_bwd.cu).  Both float32 implementations reorder millions of additions —
+        # the reference with float atomics in scheduling order, so it also moves from run to run — and a
+        # handful of ill-conditioned Gaussians out of 3 M amplify that to ~1e-4 of the tensor maximum.  The bar:
+        # this package is within GRAD_TOL of the truth wherever the reference is, and never further from the
+        # truth than the reference itself.
+        gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+        gr = {k: gr[k].clone() for k in GRAD_KEYS}
+        truth = U.truth_backward(sc, o, dLc, dLd)
+        del r, ri, rb
+        del o2
         torch.cuda.empty_cache()
         go = U.ours_backward(sc, dLc, dLd)
+        report = {}
         for k in GRAD_KEYS:
-            ref_k = gr[k].reshape(go[k].shape)
-            err, n_out = U.rel_to_max(go[k], ref_k), U.count_outliers(go[k], ref_k, GRAD_TOL)
-            assert n_out <= max(1e-5 * ref_k.numel(), 3 * ref_out[k]) and err <= 10 * GRAD_TOL, (k, err, n_out, ref_out[k])
+            e_ref = U.err_vs_truth(gr[k].reshape(go[k].shape), truth[k])
+            e_ours = U.err_vs_truth(go[k], truth[k])
+            report[k] = (e_ours, e_ref)
+        print(cfg, "gradient error vs FP64 truth (ours, reference):", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in report.items()})
+        for k, (e_ours, e_ref) in report.items():
+            assert e_ours <= max(GRAD_TOL, e_ref), (k, e_ours, e_ref, report)
+        del truth, o
         del go, gr
     else:
         del o, o2
