@@ -51,6 +51,11 @@ class DgrLayout(C.Structure):
         "img_ranges", "img_final_T", "img_n_contrib", "img_bytes")]
 
 
+class DgrAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("M", C.c_uint32), ("lr", C.c_float), ("eps", C.c_float)]
+
+
 class AdmmTensors(C.Structure):
     _fields_ = [("g", C.c_void_p * 6)]
 
@@ -68,8 +73,16 @@ SIGNATURES = {
     "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
     "dgr_sparse_adam": [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
                         C.c_uint32, C.c_uint32, _P],
+    "dgr_sparse_adam_multi": [C.POINTER(DgrAdamTensor), C.c_int32, _P, _P, C.c_float, C.c_float, C.c_uint32, _P],
     "dgr_compact_plan": [C.c_int64, _P, _P, ALLOC_FN, _P, C.POINTER(C.c_int64), _P],
     "dgr_compact_rows": [C.c_int64, C.c_int32, _P, _P, _P, _P, _P],
+    "dgr_densify_classify": [C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, ALLOC_FN, _P, C.POINTER(C.c_int64), _P],
+    "dgr_densify_plan": [C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_int32, C.c_float,
+                         C.c_int32, _P, _P, ALLOC_FN, _P, C.POINTER(C.c_int64), _P],
+    "dgr_gather_rows": [C.c_int64, C.c_int32, _P, _P, _P, _P, C.c_int32, _P],
+    "dgr_densify_split_fixup": [C.c_int64, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P, _P],
+    "dgr_reset_opacity": [C.c_int64, _P, _P, _P, C.c_float, _P],
+    "dgr_densification_stats": [C.c_int64, _P, _P, _P, _P, _P, _P],
     "fssim_forward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 6 + [_P],
     "fssim_backward": [C.c_int32] * 4 + [C.c_float, C.c_float] + [_P] * 7 + [_P],
     "fssim_l1_loss_forward": [C.c_int32] * 4 + [C.c_float] * 3 + [_P] * 5 + [_P, _P, _P],

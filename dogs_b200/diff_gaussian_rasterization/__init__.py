@@ -326,6 +326,10 @@ class SparseGaussianAdam(torch.optim.Adam):  # reference __init__.py:303-332
 
     @torch.no_grad()
     def step(self, visibility, N):
+        """visibility: bool [N] (the reference's `radii > 0`, gaussian_trainer.py:474-475) or the rasterizer's int32
+        radii themselves.  All param groups are updated by ONE kernel launch (dgr_sparse_adam_multi) where the
+        reference launches adamUpdate once per group; the arithmetic per element is the same."""
+        todo = []
         for group in self.param_groups:
             lr = group["lr"]
             eps = group["eps"]
@@ -338,10 +342,36 @@ class SparseGaussianAdam(torch.optim.Adam):  # reference __init__.py:303-332
                 state['step'] = torch.tensor(0.0, dtype=torch.float32)
                 state['exp_avg'] = torch.zeros_like(param, memory_format=torch.preserve_format)
                 state['exp_avg_sq'] = torch.zeros_like(param, memory_format=torch.preserve_format)
-            exp_avg = state["exp_avg"]
-            exp_avg_sq = state["exp_avg_sq"]
-            M = param.numel() // N
-            adamUpdate(param, param.grad, exp_avg, exp_avg_sq, visibility, lr, 0.9, 0.999, eps, N, M)
+            todo.append((param, param.grad, state["exp_avg"], state["exp_avg_sq"], lr, eps))
+        adamUpdateMulti(todo, visibility, 0.9, 0.999, N)
+
+
+def adamUpdateMulti(tensors, visible, b1, b2, N):
+    """tensors: list of (param, grad, exp_avg, exp_avg_sq, lr, eps); in-place sparse Adam step on all of them."""
+    if not tensors or N == 0:
+        return
+    dev = tensors[0][0].device
+    vis = visible.contiguous()
+    if vis.dtype not in (torch.bool, torch.int32) or vis.numel() != N:
+        raise RuntimeError("visibility must be a bool tensor, or the int32 radii, of N elements")
+    keep = []
+    for lo in range(0, len(tensors), 8):
+        chunk = tensors[lo:lo + 8]
+        arr = (L.DgrAdamTensor * len(chunk))()
+        for j, (param, grad, m, v, lr, eps) in enumerate(chunk):
+            for t in (param, m, v):
+                if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                    raise RuntimeError("adamUpdate needs contiguous float32 CUDA tensors")
+            g = grad.contiguous()
+            keep.append(g)
+            if param.numel() % N:
+                raise RuntimeError("parameter size is not a multiple of N")
+            arr[j] = L.DgrAdamTensor(param.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel() // N,
+                                     float(lr), float(eps))
+        with torch.cuda.device(dev):
+            L.check(L.lib().dgr_sparse_adam_multi(arr, len(chunk), vis.data_ptr() if vis.dtype == torch.bool else None,
+                                                  vis.data_ptr() if vis.dtype == torch.int32 else None, float(b1),
+                                                  float(b2), int(N), L.stream_ptr(dev)))
 
 
 def adamUpdate(param, param_grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps, N, M):

@@ -164,6 +164,18 @@ int dgr_sparse_adam(float* param, const float* grad, float* exp_avg, float* exp_
                     const uint8_t* visible, float lr, float b1, float b2, float eps,
                     uint32_t N, uint32_t M, void* stream);
 
+/* All parameter tensors of the model in one launch: replaces the loop of adamUpdate calls in
+ * SparseGaussianAdam.step (__init__.py:303-332).  Visibility from a bool mask (visible, [N] bytes) or straight
+ * from the rasterizer's radii (visible = radii > 0, gaussian_trainer.py:474-475); exactly one may be NULL.
+ * Tensors must be 16-byte aligned; at most 8 per call.  Same arithmetic as dgr_sparse_adam (bit-identical). */
+typedef struct DgrAdamTensor {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  uint32_t M;              /* elements per Gaussian */
+  float lr, eps;
+} DgrAdamTensor;
+int dgr_sparse_adam_multi(const DgrAdamTensor* tensors, int32_t n_tensors, const uint8_t* visible,
+                          const int32_t* radii, float b1, float b2, uint32_t N, void* stream);
+
 /* ---- stream compaction of the Gaussian SoA (prune / densify) ----------------
  * Replaces boolean-mask indexing of the 6 parameter tensors and their Adam state
  * (conerf/model/gaussian_fields/gaussian_splat_model.py:34-108,362-531). */
@@ -172,6 +184,43 @@ int dgr_compact_plan(int64_t P, const uint8_t* keep, uint32_t* offsets,
                      void* stream);
 int dgr_compact_rows(int64_t P, int32_t row_words, const void* src, void* dst,
                      const uint8_t* keep, const uint32_t* offsets, void* stream);
+
+/* ---- densification / pruning / opacity reset ---------------------------------
+ * Replace GaussianSplatModel.densify_and_prune and the methods it calls, reset_opacity and
+ * add_densification_stats (conerf/model/gaussian_fields/gaussian_splat_model.py:362-541) over the SoA.
+ * All parameter tensors are the RAW model tensors (_scaling, _opacity, _quaternion).
+ *
+ * classify (:436-443, :462-470, :502-506): cls[i] bit 0 = clone, bit 1 = split with g = accum/denom (NaN -> 0),
+ *   clone: |g| >= grad_threshold && max exp(scaling) <= scale_threshold; split: g >= grad_threshold && max > ...;
+ *   split_rank[i] = number of split Gaussians before i; *n_split_out (host) their count (one stream sync: the
+ *   caller draws the 2*n_split normal samples next, as the reference does with torch.normal).
+ * plan (:472-527): decides which of the four possible output rows of every Gaussian survive the final prune
+ *   (opacity < min_opacity; z < zmin when has_zmin; max activated scale > big_ws when big_ws >= 0) and numbers
+ *   them in the reference's order [originals not split][clones][split replicas 0][split replicas 1];
+ *   src_idx[j] / kind[j] (j < *n_out, arrays of 4*P entries) = source Gaussian / segment of output row j.
+ * gather_rows: dst[j] = src[src_idx[j]] (rows of row_words 32-bit words), or 0 where zero_new && kind[j] != 0
+ *   (Adam moments of appended rows, cat_tensors_to_optimizer :60-66).
+ * split_fixup (:472-485): xyz and scaling of the split replicas: R(q/|q|) * sample + xyz, log(exp(s) / (0.8*n)). */
+int dgr_densify_classify(int64_t P, const float* grad_accum, const float* denom, const float* raw_scaling,
+                         float grad_threshold, float scale_threshold, uint8_t* cls, uint32_t* split_rank,
+                         dogs_alloc_fn scratch_alloc, void* scratch_user, int64_t* n_split_out /* host */, void* stream);
+int dgr_densify_plan(int64_t P, const uint8_t* cls, const uint32_t* split_rank, int64_t n_split,
+                     const float* xyz, const float* raw_scaling, const float* raw_quat, const float* raw_opacity,
+                     const float* samples /* [num_replica*n_split, 3] */, float min_opacity, float big_ws,
+                     int32_t has_zmin, float zmin, int32_t num_replica, int32_t* src_idx, uint8_t* kind,
+                     dogs_alloc_fn scratch_alloc, void* scratch_user, int64_t* n_out /* host */, void* stream);
+int dgr_gather_rows(int64_t n_out, int32_t row_words, const void* src, void* dst, const int32_t* src_idx,
+                    const uint8_t* kind /* nullable */, int32_t zero_new, void* stream);
+int dgr_densify_split_fixup(int64_t n_out, const int32_t* src_idx, const uint8_t* kind, const uint32_t* split_rank,
+                            int64_t n_split, const float* xyz, const float* raw_scaling, const float* raw_quat,
+                            const float* samples, int32_t num_replica, float* xyz_out, float* scaling_out, void* stream);
+/* reset_opacity (:362-367): opacity = inverse_sigmoid(min(sigmoid(opacity), cap)) in place; the tensor's Adam
+ * moments (nullable) are zeroed (replace_tensor_to_optimizer :34-48). */
+int dgr_reset_opacity(int64_t P, float* raw_opacity, float* exp_avg, float* exp_avg_sq, float cap, void* stream);
+/* add_densification_stats (:529-541) + the trainer's max_radii2D update (gaussian_trainer.py:433-437) for the
+ * Gaussians with radii > 0: accum += |grad_means2D.xy|, denom += 1, max_radii2D (nullable) = max(., radii). */
+int dgr_densification_stats(int64_t P, const float* grad_means2D /* [P,3] */, const int32_t* radii,
+                            float* grad_accum, float* denom, float* max_radii2D, void* stream);
 
 /* ---- fused-SSIM (submodules/fused-ssim/ssim.cu:368-444) ------------------------- */
 int fssim_forward(int32_t B, int32_t CH, int32_t H, int32_t W, float C1, float C2,

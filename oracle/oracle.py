@@ -315,3 +315,90 @@ def activations(raw_opacity, raw_scaling, raw_quaternion):
     nrm = np.sqrt((sq[:, 0] + sq[:, 2]) + (sq[:, 1] + sq[:, 3]))       # torch's row-reduction order
     return o, s, (q / np.maximum(nrm, np.float32(1e-12))[:, None]).astype(np.float32)
 
+
+
+# ---- densification / pruning / opacity reset (numpy restatement of GaussianSplatModel's methods; pinned by
+# tests/golden/densify.npz, which tools/make_golden_densify.py produced by executing those methods) ----------
+DENSIFY_PARAMS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "quaternion")
+
+
+def densification_stats(accum, denom, max_radii2D, grad2d, radii):
+    """gaussian_trainer.py:433-439 + add_densification_stats (gaussian_splat_model.py:529-541), in place."""
+    vis = radii > 0
+    max_radii2D[vis] = np.maximum(max_radii2D[vis], radii[vis].astype(np.float32))
+    g = _f32(grad2d)
+    accum[vis, 0] += np.sqrt(g[vis, 0] * g[vis, 0] + g[vis, 1] * g[vis, 1]).astype(np.float32)
+    denom[vis, 0] += np.float32(1)
+
+
+def _quat_to_rot(q):
+    """conerf/model/gaussian_fields/utils.py:27-70."""
+    n = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    q = q / n[:, None]
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.zeros((q.shape[0], 3, 3), np.float32)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - r * z); R[:, 0, 2] = 2 * (x * z + r * y)
+    R[:, 1, 0] = 2 * (x * y + r * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - r * x)
+    R[:, 2, 0] = 2 * (x * z - r * y); R[:, 2, 1] = 2 * (y * z + r * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def densify_and_prune(p, m, v, accum, denom, samples, max_grad, min_opacity, extent, max_screen_size,
+                      percent_dense=0.01, bbox_zmin=None, num_replica=2):
+    """densify_and_prune (:499-527) with densify_and_clone (:433-453), densify_and_split (:455-497),
+    densification_postfix (:369-404), prune_points (:406-416) and the optimizer surgery (:34-108) on dicts of
+    numpy arrays: p parameters, m / v Adam moments.  `samples` = the torch.normal draw of :472-474.
+    Returns (p, m, v) of the new model; its statistics are all zero (postfix)."""
+    f = np.float32
+    sig = lambda o: (f(1) / (f(1) + np.exp(-o))).astype(f)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        grads = (accum / denom).astype(f)
+    grads[np.isnan(grads)] = 0
+    cat = lambda d, extra: {k: np.concatenate([d[k], extra[k]], 0) for k in DENSIFY_PARAMS}
+    zeros_like = lambda d: {k: np.zeros_like(d[k]) for k in DENSIFY_PARAMS}
+    take = lambda d, idx: {k: d[k][idx] for k in DENSIFY_PARAMS}
+    thr_scale = f(percent_dense * extent)
+    # clone
+    sel = (np.abs(grads[:, 0]) >= f(max_grad)) & (np.exp(p["scaling"]).max(1) <= thr_scale)
+    new = take(p, sel)
+    p, m, v = cat(p, new), cat(m, zeros_like(new)), cat(v, zeros_like(new))
+    # split
+    n_init = p["xyz"].shape[0]
+    padded = np.zeros(n_init, f)
+    padded[:grads.shape[0]] = grads[:, 0]
+    sel = (padded >= f(max_grad)) & (np.exp(p["scaling"]).max(1) > thr_scale)
+    R = np.tile(_quat_to_rot(p["quaternion"][sel]), (num_replica, 1, 1))
+    new = {k: np.tile(p[k][sel], (num_replica,) + (1,) * (p[k].ndim - 1)) for k in DENSIFY_PARAMS}
+    new["xyz"] = (np.einsum("nij,nj->ni", R, _f32(samples)) + np.tile(p["xyz"][sel], (num_replica, 1))).astype(f)
+    new["scaling"] = np.log(np.tile(np.exp(p["scaling"][sel]), (num_replica, 1)) / f(0.8 * num_replica)).astype(f)
+    p, m, v = cat(p, new), cat(m, zeros_like(new)), cat(v, zeros_like(new))
+    keep = ~np.concatenate([sel, np.zeros(num_replica * int(sel.sum()), bool)])
+    p, m, v = take(p, keep), take(m, keep), take(v, keep)
+    # final prune (max_radii2D was zeroed by the postfix, so the screen-size test never fires)
+    prune = sig(p["opacity"])[:, 0] < f(min_opacity)
+    if bbox_zmin is not None:
+        prune |= p["xyz"][:, 2] < f(bbox_zmin)
+    if max_screen_size is not None:
+        prune |= np.exp(p["scaling"]).max(1) > f(0.1 * extent)
+    keep = ~prune
+    return take(p, keep), take(m, keep), take(v, keep)
+
+
+def reset_opacity(opacity, cap=0.01):
+    """reset_opacity (:362-367): inverse_sigmoid(min(sigmoid(o), 0.01)); the Adam moments become zero."""
+    f = np.float32
+    x = np.minimum((f(1) / (f(1) + np.exp(-opacity))).astype(f), f(cap))
+    return np.log(x / (f(1) - x)).astype(f)
+
+
+def v_imp_score(scaling_raw, imp_list, v_pow):
+    """prune.py:14-31."""
+    volume = np.prod(np.exp(scaling_raw), axis=1)
+    kth = np.sort(volume)[::-1][int(len(volume) * 0.9)]
+    return (np.power(volume / kth, np.float32(v_pow)) * imp_list).astype(np.float32)
+
+
+def prune_by_score(score, percent):
+    """prune_gaussians_with_opt (:418-423): keep mask."""
+    s = np.sort(score)
+    return ~(score <= s[int(percent * (len(s) - 1))])

@@ -114,6 +114,38 @@ def test_sparse_adam_optimizer_class():
     assert torch.equal(U.bits(res[0]), U.bits(res[1]))
 
 
+def test_multi_tensor_sparse_adam_matches_reference_optimizer():
+    """one launch for the six parameter tensors (dgr_sparse_adam_multi) against the reference's
+    SparseGaussianAdam (six adamUpdate launches), bit for bit, with the visibility given as a bool mask and as
+    the rasterizer's int32 radii; N not a multiple of 4 so every tensor has a ragged tail."""
+    dgr, _, _ = _ref()
+    import dogs_b200.diff_gaussian_rasterization as mine
+    from dogs_b200 import _lib
+    N = 10_003
+    shapes = {"xyz": (N, 3), "f_dc": (N, 1, 3), "f_rest": (N, 15, 3), "opacity": (N, 1), "scaling": (N, 3), "quaternion": (N, 4)}
+    lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "f_rest": 1.25e-4, "opacity": 0.05, "scaling": 5e-3, "quaternion": 1e-3}
+    res = {}
+    for tag, mod, use_radii in (("ref", dgr, False), ("mask", mine, False), ("radii", mine, True)):
+        g = torch.Generator(device="cpu").manual_seed(1)
+        ps = {k: torch.randn(*s, generator=g).to(DEV).requires_grad_(True) for k, s in shapes.items()}
+        opt = mod.SparseGaussianAdam([{"params": [ps[k]], "lr": lrs[k], "name": k} for k in shapes], lr=0.0, eps=1e-15)
+        n0 = _lib.lib().dogs_launch_count()
+        for it in range(3):
+            gg = torch.Generator(device="cpu").manual_seed(10 + it)
+            for k in shapes:
+                ps[k].grad = torch.randn(*shapes[k], generator=gg).to(DEV)
+            radii = (torch.rand(N, generator=gg) * 20 - 6).to(torch.int32).clamp_min(0).to(DEV)
+            opt.step(radii if use_radii else radii > 0, N)
+        if mod is mine:
+            assert _lib.lib().dogs_launch_count() - n0 == 3          # one launch per step for all six tensors
+        res[tag] = {k: v.detach().clone() for k, v in ps.items()}
+        res[tag + "_m"] = {k: opt.state[ps[k]]["exp_avg"].clone() for k in shapes}
+    for k in shapes:
+        for tag in ("mask", "radii"):
+            assert torch.equal(U.bits(res[tag][k]), U.bits(res["ref"][k])), (tag, k)
+            assert torch.equal(U.bits(res[tag + "_m"][k]), U.bits(res["ref_m"][k])), (tag, k)
+
+
 def _virtual_plan(P, A):
     """One block whose Gaussians all have a second (virtual) owner: enough for the per-iteration penalty."""
     plan = A.BlockPlan(0, P, P)
