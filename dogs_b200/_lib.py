@@ -99,6 +99,7 @@ SIGNATURES = {
     "dogs_launch_count": [],
     "dogs_stage_timing": [C.c_int],
     "dogs_stage_times": [_P, C.c_int],
+    "dogs_forward_stage_times": [_P, C.c_int],
 }
 
 _lib = None

@@ -21,8 +21,32 @@ unsigned long long launch_count() { return g_launches; }
 // Optional per-stage device timing (dogs_stage_timing / dogs_stage_times): off by default; when on, the
 // instrumented entry points bracket their stages with CUDA events on the caller's stream and synchronise.
 static bool g_stage_timing = false;
-static float g_stage_ms[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+static float g_stage_ms[16] = {0.f};
 static int g_stage_n = 0;
+static float g_fwd_stage_ms[16] = {0.f};
+static int g_fwd_stage_n = 0;
+
+// records an event per forward stage boundary when stage timing is on
+struct StageClock {
+  cudaEvent_t ev[12];
+  int n = 0;
+  bool on;
+  cudaStream_t s;
+  StageClock(bool enabled, cudaStream_t stream) : on(enabled), s(stream) { mark(); }
+  void mark() {
+    if (!on || n >= 12) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], s);
+    n++;
+  }
+  void finish(float* out, int* count) {
+    if (!on) return;
+    cudaEventSynchronize(ev[n - 1]);
+    for (int i = 0; i + 1 < n; i++) cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]);
+    *count = n - 1;
+    for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]);
+  }
+};
 
 int check_launch(const char* what, bool debug, cudaStream_t s, int kernels) {
   g_launches += (unsigned long long)kernels;
@@ -70,13 +94,14 @@ BinState BinState::carve(char* p, size_t R) {
 }
 size_t ImgState::bytes(size_t N, size_t T) {
   Carver c(nullptr);
-  c.take<uint2>(T); c.take<float>(N); c.take<uint32_t>(N); c.take<float>(3 * N); c.take<float>(N);
+  c.take<uint2>(T); c.take<uint32_t>(T); c.take<float>(N); c.take<uint32_t>(N); c.take<float>(3 * N); c.take<float>(N);
   return c.off;
 }
 ImgState ImgState::carve(char* p, size_t N, size_t T) {
   Carver c(p);
   ImgState im;
   im.ranges = c.take<uint2>(T);
+  im.tile_order = c.take<uint32_t>(T);
   im.final_T = c.take<float>(N);
   im.n_contrib = c.take<uint32_t>(N);
   im.pix_color = c.take<float>(3 * N);
@@ -177,9 +202,11 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
 
   uint32_t R = 0;
   size_t scratch1_bytes = 0;
+  StageClock clk(g_stage_timing, s);
   if (P > 0) {
     if (launch_preprocess_fwd(p, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
                               cov3D_precomp, radii, g, s)) return 1;
+    clk.mark();   // [0] preprocess
     // depth order of the Gaussians (ties broken by index: the sort is stable)
     scratch1_bytes = align_up(P * 4) * 2 + sort_pairs_scratch_bytes(P) + scan_scratch_bytes(P) + 256;
     char* sc = scratch_alloc(scratch_user, scratch1_bytes);
@@ -194,6 +221,7 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     // 4 passes of 8 bits => the result is back in (depth_key, sorted_idx)
     if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b, true)) return 1;
     if (in_b) cudaMemcpyAsync(g.sorted_idx, vals_b, P * 4, cudaMemcpyDeviceToDevice, s);
+    clk.mark();   // [1] depth sort
     // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
     // the scan and the emit kernel then stream sequentially
     if (launch_gather_emit(p, g, s)) return 1;
@@ -203,6 +231,7 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     cudaError_t e = cudaMemcpyAsync(&R, total, 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("[CUDA ERROR] reading num_rendered: %s", cudaGetErrorString(e)); return 1; }
+    clk.mark();   // [2] gather + scan + host read of R
   }
 
   const size_t bin_bytes = BinState::bytes(R);
@@ -225,11 +254,17 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     if (passes % 2 == 0) { ka = b.tile_keys; va = b.point_list; kb = keys_u; vb = vals_u; }
     else { ka = keys_u; va = vals_u; kb = b.tile_keys; vb = b.point_list; }
     if (launch_emit(p, g, radii, ka, va, s)) return 1;
+    clk.mark();   // [3] emit
     int in_b = 0;
     if (sort_pairs_u32(ka, va, kb, vb, R, 0, bits, sort_scratch, dbg, s, &in_b)) return 1;
+    clk.mark();   // [4] tile sort
   }
   if (launch_tile_ranges(p, R, b.tile_keys, im.ranges, s)) return 1;
+  if (launch_tile_order(p, im, s)) return 1;
+  clk.mark();     // [5] ranges + order
   if (launch_blend_fwd(p, g, b, im, out_color, out_invdepth, s)) return 1;
+  clk.mark();     // [6] blend
+  clk.finish(g_fwd_stage_ms, &g_fwd_stage_n);
 
   if (info) {
     info->num_rendered = (int32_t)R;
@@ -295,11 +330,19 @@ int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3
 // Per-stage device timing for benchmarks (off by default).  While enabled, dgr_backward brackets its stages
 // with CUDA events on the caller's stream and synchronises; dogs_stage_times returns the last call's stage
 // times in ms: [0] accumulator clear + blend_bwd_kernel, [1] preprocess_bwd_kernel.
-void dogs_stage_timing(int enable) { g_stage_timing = enable != 0; g_stage_n = 0; }
+void dogs_stage_timing(int enable) { g_stage_timing = enable != 0; g_stage_n = 0; g_fwd_stage_n = 0; }
 int dogs_stage_times(float* out_ms, int n) {
   if (!out_ms || n > g_stage_n) { set_error("dogs_stage_times: %d stage(s) recorded", g_stage_n); return 1; }
   for (int i = 0; i < n; i++) out_ms[i] = g_stage_ms[i];
   return 0;
+}
+// stages of the last dgr_forward: preprocess, depth sort, gather + scan (+ host read), emit, tile sort,
+// ranges + order, blend; returns the number of stages copied (<= n), -1 when none was recorded
+int dogs_forward_stage_times(float* out_ms, int n) {
+  if (!out_ms || g_fwd_stage_n == 0) return -1;
+  const int m = n < g_fwd_stage_n ? n : g_fwd_stage_n;
+  for (int i = 0; i < m; i++) out_ms[i] = g_fwd_stage_ms[i];
+  return m;
 }
 
 int dgr_apply_activations(int32_t P, const float* raw_opacities, const float* raw_scales,

@@ -85,7 +85,8 @@ __device__ __forceinline__ int bb_slot(int lane) {
 // so the depth terms are compiled out (they would only add exact zeros).
 template <bool HAS_DEPTH>
 __global__ void __launch_bounds__(BB_THREADS)
-blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
+blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                 const uint32_t* __restrict__ point_list, int W,
                  int H, const float* __restrict__ bg_color, const SplatRecord* __restrict__ rec,
                  const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ pixel_colors, const float* __restrict__ pixel_invdepths,
@@ -106,11 +107,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   // warp w covers tile columns 8w..8w+7 (8 wide, 16 tall); pixel k of lane (lx, ly) = (lane & 7, lane >> 3)
   // is (8w + lx, 4k + ly): the 32 pixels that a warp treats together in step k form a compact 8x4
   // block, so a splat that misses the block costs the warp nothing but the test.
-  const uint32_t qx = blockIdx.x * TILE_X + 8 * warp + (lane & 7);
-  const uint32_t qy = blockIdx.y * TILE_Y + (lane >> 3);
-  const size_t HW = (size_t)H * W;
   const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
-  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+  const uint32_t tile = tile_order[blockIdx.x];     // longest list first (tile_order_kernel)
+  const uint32_t tile_x = tile % horizontal_blocks, tile_y = tile / horizontal_blocks;
+  const uint32_t qx = tile_x * TILE_X + 8 * warp + (lane & 7);
+  const uint32_t qy = tile_y * TILE_Y + (lane >> 3);
+  const size_t HW = (size_t)H * W;
+  const uint2 range = ranges[tile];
   const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
   // per-pixel state (k = 8x4 block index, top to bottom)
@@ -141,7 +144,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     // rows 0-1 of the tile = the first warp of the reference's 16x16 forward block
     if (k == 0 && (lane >> 3) < 2) lmax01 = max(lmax01, last[k]);
   }
-  const float rx0 = (float)(blockIdx.x * TILE_X + 8 * warp), ry0 = (float)(blockIdx.y * TILE_Y);
+  const float rx0 = (float)(tile_x * TILE_X + 8 * warp), ry0 = (float)(tile_y * TILE_Y);
   const float ddelx_dx = 0.5 * W;
   const float ddely_dy = 0.5 * H;
 
@@ -322,14 +325,14 @@ int launch_blend_bwd(const DgrParams& prm, const GeomState& g, const BinState& b
                      const float* dL_dcolor, const float* dL_dinvdepth, float* accum,
                      cudaStream_t s) {
   cudaMemsetAsync(accum, 0, (size_t)prm.P * BB_ACC * sizeof(float), s);
-  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
+  const uint32_t grid = ((prm.W + TILE_X - 1) / TILE_X) * ((prm.H + TILE_Y - 1) / TILE_Y);
   if (dL_dinvdepth)
-    blend_bwd_kernel<true><<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
+    blend_bwd_kernel<true><<<grid, BB_THREADS, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, prm.bg, g.rec,
                                                im.final_T, im.n_contrib, im.pix_color,
                                                im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
                                                prm.ref_bucket_cull_quirk != 0);
   else
-    blend_bwd_kernel<false><<<grid, BB_THREADS, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, prm.bg, g.rec,
+    blend_bwd_kernel<false><<<grid, BB_THREADS, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, prm.bg, g.rec,
                                                im.final_T, im.n_contrib, im.pix_color,
                                                im.pix_invdepth, dL_dcolor, dL_dinvdepth, accum,
                                                prm.ref_bucket_cull_quirk != 0);

@@ -25,7 +25,8 @@ namespace dogs {
 // tiles add up in shared memory and one integer atomic per (tile, Gaussian) reaches global memory).
 template <bool COUNT>
 __global__ void __launch_bounds__(TILE_PIX)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W,
+blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                 const uint32_t* __restrict__ point_list, int W,
                  int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                  float* __restrict__ out_color, float* __restrict__ invdepth,
@@ -40,8 +41,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const uint32_t tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
+  // CTAs are launched longest list first (tile_order_kernel)
+  const uint32_t tile = tile_order[blockIdx.x];
+  const uint32_t tile_x = tile % horizontal_blocks, tile_y = tile / horizontal_blocks;
   // warp -> 8x4 block (2 columns x 4 rows of blocks per tile); lane -> pixel inside the block
-  const uint32_t bx0 = blockIdx.x * TILE_X + (warp & 1) * 8, by0 = blockIdx.y * TILE_Y + (warp >> 1) * 4;
+  const uint32_t bx0 = tile_x * TILE_X + (warp & 1) * 8, by0 = tile_y * TILE_Y + (warp >> 1) * 4;
   const uint2 pix = {bx0 + (lane & 7), by0 + (lane >> 3)};
   const uint32_t pix_id = W * pix.y + pix.x;
   const float2 pixf = {(float)pix.x, (float)pix.y};
@@ -49,7 +53,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   bool done = !inside;
   const float rx0 = (float)bx0, ry0 = (float)by0, rx1 = (float)(bx0 + 7), ry1 = (float)(by0 + 3);
 
-  const uint2 range = ranges[blockIdx.y * horizontal_blocks + blockIdx.x];
+  const uint2 range = ranges[tile];
   const int rounds = ((range.y - range.x + TILE_PIX - 1) / TILE_PIX);
   int toDo = range.y - range.x;
 
@@ -170,17 +174,17 @@ __global__ void importance_kernel(int P, const int* __restrict__ count, const Sp
 
 int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
                      float* out_color, float* out_invdepth, cudaStream_t s) {
-  dim3 grid((prm.W + TILE_X - 1) / TILE_X, (prm.H + TILE_Y - 1) / TILE_Y, 1);
+  const uint32_t grid = ((prm.W + TILE_X - 1) / TILE_X) * ((prm.H + TILE_Y - 1) / TILE_Y);
   if (prm.gaussians_count) {
     cudaMemsetAsync(prm.gaussians_count, 0, (size_t)prm.P * sizeof(int32_t), s);
-    blend_fwd_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+    blend_fwd_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, g.rec, prm.bg,
                                                      im.final_T, im.n_contrib, out_color, out_invdepth,
                                                      im.pix_color, im.pix_invdepth, prm.gaussians_count);
     if (prm.important_score)
       importance_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, prm.gaussians_count, g.rec, prm.important_score);
     return check_launch("blend_fwd(count)", prm.debug != 0, s, prm.important_score ? 2 : 1);
   }
-  blend_fwd_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, prm.W, prm.H, g.rec, prm.bg,
+  blend_fwd_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, g.rec, prm.bg,
                                                     im.final_T, im.n_contrib, out_color, out_invdepth,
                                                     im.pix_color, im.pix_invdepth, nullptr);
   return check_launch("blend_fwd", prm.debug != 0, s);

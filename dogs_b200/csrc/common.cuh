@@ -205,7 +205,8 @@ struct BinState {
   static BinState carve(char* p, size_t R);
 };
 struct ImgState {
-  uint2* ranges; float* final_T; uint32_t* n_contrib;
+  uint2* ranges; uint32_t* tile_order;   // tile ids, longest list first: the launch order of the blend kernels
+  float* final_T; uint32_t* n_contrib;
   float* pix_color; float* pix_invdepth;  // forward outputs kept for the backward replay
   static size_t bytes(size_t N, size_t T);
   static ImgState carve(char* p, size_t N, size_t T);
@@ -234,6 +235,7 @@ int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, 
                 uint32_t* vals, cudaStream_t s);
 int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,
                        cudaStream_t s);
+int launch_tile_order(const DgrParams& prm, const ImgState& im, cudaStream_t s);
 int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
                      float* out_color, float* out_invdepth, cudaStream_t s);
 int launch_activations(int P, const float* raw_op, const float* raw_sc, const float* raw_rot, float* op,

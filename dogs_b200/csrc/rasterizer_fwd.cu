@@ -3,6 +3,7 @@
 // alpha blend.  Arithmetic follows cuda_rasterizer/forward.cu:24-276,349-501 and
 // rasterizer_impl.cu:52-220 operation by operation so that radii, keys,
 // ranges, n_contrib and final_T come out bit-identical; the kernel structure does not.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dogs {
@@ -415,6 +416,59 @@ tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys, uint2* __
   }
 }
 
+// Launch order of the per-tile blend kernels: tile ids by list length, longest first.  List lengths are
+// heavy-tailed (a few tiles hold 5-10x the mean), and with one CTA per tile in row-major order the long ones
+// that happen to come last leave most SMs idle while they finish.  One CTA bins the T lengths into 1024 buckets
+// (approximate order is all the scheduler needs) and writes the permutation.
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(uint32_t T, const uint2* __restrict__ ranges, uint32_t* __restrict__ order) {
+  __shared__ uint32_t bins[1024];
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t smax;
+  const uint32_t tid = threadIdx.x;
+  bins[tid] = 0;
+  if (tid == 0) smax = 0;
+  __syncthreads();
+  uint32_t m = 0;
+  for (uint32_t t = tid; t < T; t += 1024) m = max(m, ranges[t].y - ranges[t].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) atomicMax(&smax, m);
+  __syncthreads();
+  const float scale = 1023.0f / (float)max(smax, 1u);
+  for (uint32_t t = tid; t < T; t += 1024) {
+    const uint32_t len = ranges[t].y - ranges[t].x;
+    atomicAdd(&bins[1023u - min(1023u, (uint32_t)((float)len * scale))], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 bins (one per thread)
+  const uint32_t v = bins[tid];
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((tid & 31) >= (uint32_t)o) x += y;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = x;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = wsum[tid], y2 = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, y2, o);
+      if (tid >= (uint32_t)o) y2 += y;
+    }
+    wsum[tid] = y2 - w;
+  }
+  __syncthreads();
+  bins[tid] = wsum[tid >> 5] + x - v;
+  __syncthreads();
+  for (uint32_t t = tid; t < T; t += 1024) {
+    const uint32_t len = ranges[t].y - ranges[t].x;
+    order[atomicAdd(&bins[1023u - min(1023u, (uint32_t)((float)len * scale))], 1u)] = t;
+  }
+}
+
 // ---- visible_filter / mark_visible ---------------------------------------------------
 // filter_preprocessCUDA (forward.cu:279-344): radii only, without the +0.3 low-pass.
 __global__ void __launch_bounds__(256)
@@ -521,6 +575,19 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_ke
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
   if (R > 0) tile_ranges_kernel<<<(R + 1023) / 1024, 256, 0, s>>>(R, tile_keys, ranges);
   return check_launch("tile_ranges", prm.debug != 0, s);
+}
+
+__global__ void tile_identity_kernel(uint32_t T, uint32_t* __restrict__ order) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) order[t] = t;
+}
+
+int launch_tile_order(const DgrParams& prm, const ImgState& im, cudaStream_t s) {
+  const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
+  static const bool by_length = !(getenv("DOGS_B200_TILE_ORDER") && getenv("DOGS_B200_TILE_ORDER")[0] == '0');
+  if (by_length) tile_order_kernel<<<1, 1024, 0, s>>>(gx * gy, im.ranges, im.tile_order);
+  else tile_identity_kernel<<<(gx * gy + 255) / 256, 256, 0, s>>>(gx * gy, im.tile_order);
+  return check_launch("tile_order", prm.debug != 0, s);
 }
 
 __global__ void activations_kernel(int P, const float* __restrict__ raw_op, const float* __restrict__ raw_sc,

@@ -314,6 +314,9 @@ unsigned long long dogs_launch_count(void);
  * [0] accumulator clear + blend_bwd_kernel, [1] preprocess_bwd_kernel. */
 void dogs_stage_timing(int enable);
 int dogs_stage_times(float* out_ms, int n);
+/* the same for the last dgr_forward: preprocess, depth sort, gather + scan, emit, tile sort, ranges + order,
+ * blend (ms); returns the number of stages copied, -1 when none was recorded */
+int dogs_forward_stage_times(float* out_ms, int n);
 
 #ifdef __cplusplus
 }

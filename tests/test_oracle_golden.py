@@ -244,4 +244,5 @@ def test_count_render_oracle_vs_old_rasterizer_golden(name):
     diff = np.abs(o["gaussians_count"].astype(np.int64) - g["gaussians_count"])
     assert int(diff.sum()) <= max(8, int(g["gaussians_count"].sum()) // 20000)
     same = diff == 0
-    assert np.allclose(o["important_score"][same], g["important_score"][same], rtol=2e-6, atol=1e-7)
+    # the reference adds `opacity` once per blended pixel in float32 (count roundings); count * opacity has one
+    assert np.allclose(o["important_score"][same], g["important_score"][same], rtol=1e-5, atol=1e-7)

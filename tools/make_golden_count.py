@@ -36,7 +36,7 @@ def run(mod, sc):
     rs = mod.GaussianRasterizationSettings(
         image_height=int(sc["H"]), image_width=int(sc["W"]), tanfovx=sc["tanfovx"], tanfovy=sc["tanfovy"],
         bg=torch.zeros(3, device=DEV), scale_modifier=1.0, viewmatrix=sc["viewmatrix"], projmatrix=sc["projmatrix"],
-        sh_degree=3, campos=sc["campos"], prefiltered=False, debug=False, f_count=True)
+        sh_degree=3, campos=sc["campos"], prefiltered=False, debug=False, depth_threshold=0.0, f_count=True)
     shs = torch.cat([sc["dc"], sc["sh"]], dim=1).contiguous()
     cnt, score, color, radii = mod.GaussianRasterizer(rs)(
         means3D=sc["means3D"], means2D=torch.zeros_like(sc["means3D"]), opacities=sc["opacities"], shs=shs,
