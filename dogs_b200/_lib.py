@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdogs_b200.so")
+LIB_PATH = os.environ.get("DOGS_B200_LIB") or os.path.join(_HERE, "libdogs_b200.so")     # override: A/B experiments
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -33,6 +33,7 @@ class DgrParams(C.Structure):
         ("ref_bucket_cull_quirk", C.c_int32), ("raw_inputs", C.c_int32),
         ("admm", C.POINTER(DgrAdmmPenalty)),
         ("gaussians_count", C.c_void_p), ("important_score", C.c_void_p),
+        ("instance_capacity", C.c_int32), ("depth_key_bits", C.c_int32),
     ]
 
 
@@ -41,6 +42,7 @@ class DgrForwardInfo(C.Structure):
         ("num_rendered", C.c_int32), ("num_visible", C.c_int32),
         ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t),
         ("image_bytes", C.c_size_t), ("scratch_bytes", C.c_size_t),
+        ("depth_key_bits", C.c_int32), ("binning_rows", C.c_int32),
     ]
 
 

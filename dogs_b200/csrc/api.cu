@@ -1,6 +1,7 @@
 // C-ABI entry points of the rasterizer (include/dogs_b200.h).  Host orchestration only:
 // carves the caller-allocated buffers, launches the stage kernels on the caller's stream.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -13,6 +14,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("DOGS_B200_PDL") && getenv("DOGS_B200_PDL")[0] == '0');
+  return on;
 }
 
 static unsigned long long g_launches = 0;
@@ -64,6 +70,7 @@ size_t GeomState::bytes(size_t P) {
   Carver c(nullptr);
   c.take<SplatRecord>(P); c.take<uint8_t>(P); c.take<uint32_t>(P); c.take<uint32_t>(P);
   c.take<uint32_t>(P); c.take<uint32_t>(P); c.take<uint4>(P); c.take<uint4>(P); c.take<uint32_t>(P);
+  c.take<uint32_t>(16);
   return c.off;
 }
 GeomState GeomState::carve(char* p, size_t P) {
@@ -78,6 +85,7 @@ GeomState GeomState::carve(char* p, size_t P) {
   g.emit_rec = c.take<uint4>(P);
   g.sorted_emit = c.take<uint4>(P);
   g.sorted_cnt = c.take<uint32_t>(P);
+  g.ctl = c.take<uint32_t>(16);
   return g;
 }
 size_t BinState::bytes(size_t R) {
@@ -107,6 +115,24 @@ ImgState ImgState::carve(char* p, size_t N, size_t T) {
   im.pix_color = c.take<float>(3 * N);
   im.pix_invdepth = c.take<float>(N);
   return im;
+}
+
+// Pinned host word + side stream + events used to read the instance count back without stalling the stream
+// the kernels run on.  One per (host thread, device), created on first use.
+struct HostReadback { uint32_t* pinned; cudaStream_t side; cudaEvent_t ev_ready, ev_done; bool ok; };
+static HostReadback* readback() {
+  static thread_local HostReadback slots[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostReadback& r = slots[dev];
+  if (!r.ok) {
+    if (cudaHostAlloc((void**)&r.pinned, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.ev_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    r.ok = true;
+  }
+  return &r;
 }
 
 // getHigherMsb (rasterizer_impl.cu:35-50): number of bits needed for tile ids, 2^bit > T.
@@ -200,10 +226,62 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
   GeomState g = GeomState::carve(geom_p, P);
   ImgState im = ImgState::carve(img_p, N, T);
 
-  uint32_t R = 0;
-  size_t scratch1_bytes = 0;
+  // The instance count R is produced on the device (exclusive-scan total).  Sizing the binning buffers by it
+  // costs a host round trip in the middle of the pass (the reference has two: rasterizer_impl.cu:423,469).  With
+  // DgrParams::instance_capacity > 0 the buffers are allocated for that many rows BEFORE anything is launched,
+  // every kernel after the scan takes R from device memory, the whole pass is enqueued without waiting, and R is
+  // copied to pinned host memory on a side stream while the emit / tile-sort / blend kernels run.  The host
+  // looks at it only at the end: the GPU never idles.  R > capacity (kernels clamp, nothing is written out of
+  // bounds) re-runs the stages after the scan with exactly sized buffers.
+  uint32_t R = 0, rows = 0;
+  int key_bits = 0;
+  size_t scratch1_bytes = 0, scratch2_bytes = 0;
   StageClock clk(g_stage_timing, s);
+  HostReadback* rb = readback();
+  if (!rb) { set_error("forward: cannot create the pinned read-back slot"); return 1; }
+  const int bits = higher_msb((uint32_t)T);
+  const int passes = (bits + 7) / 8;
+  BinState b = BinState::carve(nullptr, 0);
+  size_t bin_bytes = 0;
+
+  // stages after the scan, for a binning buffer of `cap` rows; dev_count: take R from g.ctl[2]
+  auto bin_and_blend = [&](uint32_t cap, bool dev_count) -> int {
+    bin_bytes = BinState::bytes(cap);
+    char* bin_p = binning_alloc(binning_user, bin_bytes > 0 ? bin_bytes : 256);
+    if (!bin_p) { set_error("binning allocation failed"); return 1; }
+    b = BinState::carve(bin_p, cap);
+    rows = cap;
+    const uint32_t* R_dev = dev_count ? g.ctl + 2 : nullptr;
+    if (cap > 0) {
+      scratch2_bytes = align_up((size_t)cap * 4) * 2 + sort_pairs_scratch_bytes(cap) + 256;
+      char* sc = scratch_alloc(scratch_user, scratch2_bytes);
+      if (!sc) { set_error("scratch allocation failed"); return 1; }
+      Carver cv(sc);
+      uint32_t* keys_u = cv.take<uint32_t>(cap);
+      uint32_t* vals_u = cv.take<uint32_t>(cap);
+      char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(cap));
+      // arrange the ping-pong so that the last pass lands in the persistent binning buffers
+      uint32_t *ka, *va, *kb, *vb;
+      if (passes % 2 == 0) { ka = b.tile_keys; va = b.point_list; kb = keys_u; vb = vals_u; }
+      else { ka = keys_u; va = vals_u; kb = b.tile_keys; vb = b.point_list; }
+      if (launch_emit(p, g, radii, ka, va, cap, s)) return 1;
+      clk.mark();   // [3] emit
+      int in_b = 0;
+      const SortCtl ctl_t{R_dev};
+      if (sort_pairs_u32(ka, va, kb, vb, cap, 0, bits, sort_scratch, dbg, s, &in_b, false, &ctl_t)) return 1;
+      clk.mark();   // [4] tile sort
+    }
+    if (launch_tile_ranges(p, cap, R_dev, b.tile_keys, im.ranges, s)) return 1;
+    if (launch_tile_order(p, im, s)) return 1;
+    clk.mark();     // [5] ranges + order
+    if (launch_blend_fwd(p, g, b, im, out_color, out_invdepth, s)) return 1;
+    clk.mark();     // [6] blend
+    return 0;
+  };
+
   if (P > 0) {
+    cudaMemsetAsync(g.ctl, 0, 16 * sizeof(uint32_t), s);
+    cudaMemsetAsync(g.ctl, 0xff, sizeof(uint32_t), s);          // ctl[0] = smallest depth key so far
     if (launch_preprocess_fwd(p, means3D, dc, sh, colors_precomp, opacities, scales, rotations,
                               cov3D_precomp, radii, g, s)) return 1;
     clk.mark();   // [0] preprocess
@@ -214,61 +292,55 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     Carver cv(sc);
     uint32_t* keys_b = cv.take<uint32_t>(P);
     uint32_t* vals_b = cv.take<uint32_t>(P);
-    uint32_t* total = cv.take<uint32_t>(1);
     char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(P));
     char* scan_scratch = cv.take<char>(scan_scratch_bytes(P));
-    int in_b = 0;
-    // 4 passes of 8 bits => the result is back in (depth_key, sorted_idx)
-    if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, 32, sort_scratch, dbg, s, &in_b, true)) return 1;
-    if (in_b) cudaMemcpyAsync(g.sorted_idx, vals_b, P * 4, cudaMemcpyDeviceToDevice, s);
-    clk.mark();   // [1] depth sort
-    // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
-    // the scan and the emit kernel then stream sequentially
-    if (launch_gather_emit(p, g, s)) return 1;
-    if (exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, total, P, scan_scratch, dbg, s)) return 1;
-    // the one host synchronisation of the forward pass (the reference has two:
-    // rasterizer_impl.cu:423,469): the instance count sizes the binning buffers.
-    cudaError_t e = cudaMemcpyAsync(&R, total, 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    // Depth order.  Positive floats of one scene share their top bits, so only the low `key_bits` bits — up to
+    // the highest bit in which the smallest and the largest key differ — need sorting (3 passes of 8 bits instead
+    // of 4 for depths within a factor of ~2-4).  The host cannot know that range yet, so it sorts on the bits the
+    // CALLER expects (DgrParams::depth_key_bits, learnt from earlier frames), reads the true range back together
+    // with the instance count, and repeats the depth stage on all 32 bits in the (rare) case it was wider.
+    // Culled Gaussians carry the key 0xffffffff: on any bit range they sort last among equals and own no instances.
+    auto depth_stage = [&](int key_bits) -> int {
+      int in_b = 0;
+      if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, key_bits, sort_scratch, dbg, s, &in_b, true)) return 1;
+      clk.mark();   // [1] depth sort
+      // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
+      // the scan and the emit kernel then stream sequentially
+      if (launch_gather_emit(p, g, in_b ? vals_b : g.sorted_idx, s)) return 1;
+      return exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, g.ctl + 2, P, scan_scratch, dbg, s);
+    };
+    const int bits_assumed = (p.depth_key_bits >= 1 && p.depth_key_bits <= 32) ? p.depth_key_bits : 32;
+    if (depth_stage(bits_assumed)) return 1;
+    // {smallest key, largest key, R} -> pinned host memory on the side stream
+    cudaError_t e = cudaEventRecord(rb->ev_ready, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(rb->side, rb->ev_ready, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rb->pinned, g.ctl, 12, cudaMemcpyDeviceToHost, rb->side);
+    if (e == cudaSuccess) e = cudaEventRecord(rb->ev_done, rb->side);
+    const bool optimistic = p.instance_capacity > 0;
+    if (e == cudaSuccess && optimistic) {
+      clk.mark();   // [2] gather + scan
+      if (bin_and_blend((uint32_t)p.instance_capacity, true)) return 1;
+    }
+    if (e == cudaSuccess) e = cudaEventSynchronize(rb->ev_done);
     if (e != cudaSuccess) { set_error("[CUDA ERROR] reading num_rendered: %s", cudaGetErrorString(e)); return 1; }
-    clk.mark();   // [2] gather + scan + host read of R
+    key_bits = significant_key_bits(rb->pinned[0], rb->pinned[1]);
+    const bool redo_depth = key_bits > bits_assumed;
+    if (redo_depth && (launch_depth_keys(p, g, s) || depth_stage(32))) return 1;
+    R = rb->pinned[2];
+    if (!optimistic) clk.mark();   // [2] gather + scan + host read of R
+    if (!optimistic || redo_depth || R > (uint32_t)p.instance_capacity) {
+      if (bin_and_blend(R, false)) return 1;
+    }
+  } else {
+    if (bin_and_blend(0, false)) return 1;
   }
-
-  const size_t bin_bytes = BinState::bytes(R);
-  char* bin_p = binning_alloc(binning_user, bin_bytes > 0 ? bin_bytes : 256);
-  if (!bin_p) { set_error("binning allocation failed"); return 1; }
-  BinState b = BinState::carve(bin_p, R);
-  size_t scratch2_bytes = 0;
-  if (R > 0) {
-    scratch2_bytes = align_up((size_t)R * 4) * 2 + sort_pairs_scratch_bytes(R) + 256;
-    char* sc = scratch_alloc(scratch_user, scratch2_bytes);
-    if (!sc) { set_error("scratch allocation failed"); return 1; }
-    Carver cv(sc);
-    uint32_t* keys_u = cv.take<uint32_t>(R);
-    uint32_t* vals_u = cv.take<uint32_t>(R);
-    char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(R));
-    const int bits = higher_msb((uint32_t)T);
-    const int passes = (bits + 7) / 8;
-    // arrange the ping-pong so that the last pass lands in the persistent binning buffers
-    uint32_t *ka, *va, *kb, *vb;
-    if (passes % 2 == 0) { ka = b.tile_keys; va = b.point_list; kb = keys_u; vb = vals_u; }
-    else { ka = keys_u; va = vals_u; kb = b.tile_keys; vb = b.point_list; }
-    if (launch_emit(p, g, radii, ka, va, s)) return 1;
-    clk.mark();   // [3] emit
-    int in_b = 0;
-    if (sort_pairs_u32(ka, va, kb, vb, R, 0, bits, sort_scratch, dbg, s, &in_b)) return 1;
-    clk.mark();   // [4] tile sort
-  }
-  if (launch_tile_ranges(p, R, b.tile_keys, im.ranges, s)) return 1;
-  if (launch_tile_order(p, im, s)) return 1;
-  clk.mark();     // [5] ranges + order
-  if (launch_blend_fwd(p, g, b, im, out_color, out_invdepth, s)) return 1;
-  clk.mark();     // [6] blend
   clk.finish(g_fwd_stage_ms, &g_fwd_stage_n);
 
   if (info) {
     info->num_rendered = (int32_t)R;
     info->num_visible = -1;
+    info->binning_rows = (int32_t)rows;
+    info->depth_key_bits = key_bits;
     info->geom_bytes = geom_bytes;
     info->binning_bytes = bin_bytes;
     info->image_bytes = img_bytes;

@@ -38,6 +38,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ uint32_t sId[COUNT ? 2 : 1][COUNT ? TILE_PIX : 1];
   __shared__ int sCnt[COUNT ? TILE_PIX : 1];
   if (COUNT) sCnt[threadIdx.x] = 0;
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t horizontal_blocks = (W + TILE_X - 1) / TILE_X;
@@ -184,9 +186,9 @@ int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b
       importance_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, prm.gaussians_count, g.rec, prm.important_score);
     return check_launch("blend_fwd(count)", prm.debug != 0, s, prm.important_score ? 2 : 1);
   }
-  blend_fwd_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, g.rec, prm.bg,
-                                                    im.final_T, im.n_contrib, out_color, out_invdepth,
-                                                    im.pix_color, im.pix_invdepth, nullptr);
+  launch_pdl(blend_fwd_kernel<false>, dim3(grid), dim3(TILE_PIX), 0, s, (const uint2*)im.ranges, (const uint32_t*)im.tile_order,
+             (const uint32_t*)b.point_list, (int)prm.W, (int)prm.H, (const SplatRecord*)g.rec, prm.bg, im.final_T, im.n_contrib,
+             out_color, out_invdepth, im.pix_color, im.pix_invdepth, (int*)nullptr);
   return check_launch("blend_fwd", prm.debug != 0, s);
 }
 

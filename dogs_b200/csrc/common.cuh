@@ -186,6 +186,32 @@ template <typename K> static void allow_big_smem(K kernel, bool (&done)[64]) {
   }
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------------
+// The rasterizer is a chain of ~30 short kernels per step, each depending on the previous one.  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, a kernel may be scheduled while its predecessor is still
+// draining; it calls pdl_wait() (griddepcontrol.wait: returns once the predecessor grid has completed and its
+// writes are visible) before it touches anything the predecessor produced, so the launch latency and the
+// prologue overlap the predecessor's tail.  pdl_trigger() lets the successor be scheduled as early as possible.
+// Both are no-ops for a kernel launched the ordinary way.  DOGS_B200_PDL=0 switches the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- stage launchers (defined in the .cu files) -----------------------------------
 struct GeomState {
   SplatRecord* rec; uint8_t* clamped; uint32_t* tiles; uint32_t* depth_key;
@@ -196,6 +222,9 @@ struct GeomState {
   uint4* emit_rec;
   uint4* sorted_emit;      // the same in depth order, .y replaced by the Gaussian id
   uint32_t* sorted_cnt;    // instance counts in depth order (scan input)
+  // device-side control words: [0] smallest, [1] largest depth key of the Gaussians that emit instances,
+  // [2] number of tile instances R (exclusive-scan total), [3] 1 = R exceeded the binning capacity
+  uint32_t* ctl;
   static size_t bytes(size_t P);
   static GeomState carve(char* p, size_t P);
 };
@@ -213,12 +242,25 @@ struct ImgState {
 };
 
 // radix_sort.cu
+// Optional device-side control of a sort (passed to the kernels by value):
+//   n_dev  element count in device memory, or null: the launch is sized for the host-side capacity `n`, the
+//          kernels use min(*n_dev, n).
+struct SortCtl { const uint32_t* n_dev; };
+// number of low bits in which two keys can differ, given the smallest and largest of them (>= 1)
+static inline int significant_key_bits(uint32_t kmin, uint32_t kmax) {
+  if (kmin >= kmax) return 1;
+  uint32_t d = kmin ^ kmax;
+  int hb = 0;
+  while (d) { hb++; d >>= 1; }
+  return hb;
+}
 size_t sort_pairs_scratch_bytes(size_t n);
 // Stable LSD sort of (key,val) u32 pairs on bits [begin_bit,end_bit), 8 bits per pass, ping-pong
 // between the (a) and (b) buffers starting from (a); *result_in_b tells where the result is.
 int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                    size_t n, int begin_bit, int end_bit, char* scratch, bool debug, cudaStream_t s,
-                   int* result_in_b, bool vals_are_iota = false);   // true: vals_a is treated as 0..n-1 and never read
+                   int* result_in_b, bool vals_are_iota = false,   // true: vals_a is treated as 0..n-1 and never read
+                   const SortCtl* ctl = nullptr);
 size_t scan_scratch_bytes(size_t n);
 // out[i] = sum_{j<i} in[idx ? idx[j] : j]; total (may be null) receives the grand total.
 int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* total,
@@ -230,11 +272,13 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
                           const float* sh, const float* colors_precomp, const float* opacities,
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           int32_t* radii, GeomState& g, cudaStream_t s);
-int launch_gather_emit(const DgrParams& prm, const GeomState& g, cudaStream_t s);
+int launch_depth_keys(const DgrParams& prm, const GeomState& g, cudaStream_t s);
+int launch_gather_emit(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, cudaStream_t s);
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
-                uint32_t* vals, cudaStream_t s);
-int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,
-                       cudaStream_t s);
+                uint32_t* vals, uint32_t capacity, cudaStream_t s);
+// R_cap: rows the launch is sized for; R_dev (nullable): actual count in device memory
+int launch_tile_ranges(const DgrParams& prm, uint32_t R_cap, const uint32_t* R_dev, const uint32_t* tile_keys,
+                       uint2* ranges, cudaStream_t s);
 int launch_tile_order(const DgrParams& prm, const ImgState& im, cudaStream_t s);
 int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b, const ImgState& im,
                      float* out_color, float* out_invdepth, cudaStream_t s);

@@ -19,9 +19,18 @@ constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 
+// Device-side element count (SortCtl, common.cuh): the forward pass no longer waits for the host to read the
+// instance count, so the tile sort is launched for the buffer capacity and takes the count from device memory.
+__device__ __forceinline__ uint32_t sort_count(const SortCtl ctl, uint32_t n_cap) {
+  return ctl.n_dev ? min(*ctl.n_dev, n_cap) : n_cap;
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t mask,
-                  uint32_t* __restrict__ hist, uint32_t nblk) {
+radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_cap, int shift, uint32_t mask,
+                  uint32_t* __restrict__ hist, uint32_t nblk, const SortCtl ctl) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t n = sort_count(ctl, n_cap);
   __shared__ uint32_t h[RADIX];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -38,6 +47,8 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint
 // One CTA per digit: exclusive scan of that digit's per-block counts, digit total to totals[d].
 __global__ void __launch_bounds__(256)
 radix_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblk, uint32_t* __restrict__ totals) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t wsum[8];
   __shared__ uint32_t carry_s;
   uint32_t* row = hist + (size_t)blockIdx.x * nblk;
@@ -73,9 +84,13 @@ radix_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblk, uint32_t* __res
 // scatter stores, which is what bounded the first version of this kernel (ncu: issue-active 9 %).
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_cap,
                      int shift, uint32_t mask, const uint32_t* __restrict__ hist, uint32_t nblk,
-                     const uint32_t* __restrict__ totals) {
+                     const uint32_t* __restrict__ totals, const SortCtl ctl) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t n = sort_count(ctl, n_cap);
+  if (blockIdx.x * SORT_CHUNK >= n) return;
   __shared__ uint32_t cnt[SORT_WARPS][RADIX];
   __shared__ uint32_t lbase[RADIX];
   __shared__ uint32_t gbase[RADIX];
@@ -189,7 +204,8 @@ size_t sort_pairs_scratch_bytes(size_t n) {
 
 int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                    size_t n, int begin_bit, int end_bit, char* scratch, bool debug,
-                   cudaStream_t s, int* result_in_b, bool vals_are_iota) {
+                   cudaStream_t s, int* result_in_b, bool vals_are_iota, const SortCtl* ctl_in) {
+  const SortCtl ctl = ctl_in ? *ctl_in : SortCtl{nullptr};
   *result_in_b = 0;
   if (n == 0 || end_bit <= begin_bit) return 0;
   uint32_t nblk = (uint32_t)((n + SORT_CHUNK - 1) / SORT_CHUNK);
@@ -200,10 +216,11 @@ int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_
   for (int b = begin_bit; b < end_bit; b += 8) {
     int nb = end_bit - b < 8 ? end_bit - b : 8;
     uint32_t mask = (1u << nb) - 1u;
-    radix_hist_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, (uint32_t)n, b, mask, hist, nblk);
-    radix_rowscan_kernel<<<RADIX, 256, 0, s>>>(hist, nblk, totals);
-    radix_scatter_kernel<<<nblk, SORT_THREADS, 0, s>>>(ki, (vals_are_iota && b == begin_bit) ? nullptr : vi, ko, vo,
-                                                      (uint32_t)n, b, mask, hist, nblk, totals);
+    launch_pdl(radix_hist_kernel, dim3(nblk), dim3(SORT_THREADS), 0, s, ki, (uint32_t)n, b, mask, hist, nblk, ctl);
+    launch_pdl(radix_rowscan_kernel, dim3(RADIX), dim3(256), 0, s, hist, nblk, totals);
+    launch_pdl(radix_scatter_kernel, dim3(nblk), dim3(SORT_THREADS), 0, s, ki,
+               (vals_are_iota && b == begin_bit) ? (const uint32_t*)nullptr : (const uint32_t*)vi, ko, vo, (uint32_t)n, b, mask,
+               hist, nblk, totals, ctl);
     if (int e = check_launch("radix pass", debug, s, 3)) return e;
     uint32_t* t;
     t = ki; ki = ko; ko = t;
@@ -243,6 +260,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_reduce_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ idx, uint32_t n,
                    uint32_t* __restrict__ partial) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t wsum[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS, sum = 0;
 #pragma unroll
@@ -257,6 +276,8 @@ scan_reduce_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_spine_kernel(uint32_t* __restrict__ partial, uint32_t nb, uint32_t* __restrict__ total_out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t wsum[SCAN_THREADS / 32];
   uint32_t carry = 0;
   for (uint32_t start = 0; start < nb; start += SCAN_THREADS) {
@@ -272,6 +293,8 @@ scan_spine_kernel(uint32_t* __restrict__ partial, uint32_t nb, uint32_t* __restr
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ idx, uint32_t n,
                   const uint32_t* __restrict__ partial, uint32_t* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t wsum[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS], sum = 0;
@@ -303,9 +326,9 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, u
   }
   uint32_t nb = (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
   uint32_t* partial = reinterpret_cast<uint32_t*>(scratch);
-  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial);
-  scan_spine_kernel<<<1, SCAN_THREADS, 0, s>>>(partial, nb, total);
-  scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, idx, (uint32_t)n, partial, out);
+  launch_pdl(scan_reduce_kernel, dim3(nb), dim3(SCAN_THREADS), 0, s, in, idx, (uint32_t)n, partial);
+  launch_pdl(scan_spine_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, partial, nb, total);
+  launch_pdl(scan_apply_kernel, dim3(nb), dim3(SCAN_THREADS), 0, s, in, idx, (uint32_t)n, (const uint32_t*)partial, out);
   return check_launch("exclusive scan", debug, s, 3);
 }
 

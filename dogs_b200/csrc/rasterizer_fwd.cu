@@ -106,6 +106,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       int* __restrict__ radii, SplatRecord* __restrict__ rec,
                       uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
                       uint32_t* __restrict__ depth_key, uint4* __restrict__ emit_rec,
+                      uint32_t* __restrict__ ctl,
                       uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing, bool raw_inputs) {
   extern __shared__ float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
@@ -264,6 +265,23 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       }
     }
   }
+  // range of the depth keys that take part in the sort (ctl[0] = min, ctl[1] = max): one reduction per CTA
+  {
+    __shared__ uint32_t s_min[PRE_THREADS / 32], s_max[PRE_THREADS / 32];
+    uint32_t kmin = (idx < P && ntiles) ? dkey : 0xffffffffu, kmax = (idx < P && ntiles) ? dkey : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = kmin; s_max[threadIdx.x >> 5] = kmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < PRE_THREADS / 32; w++) { kmin = min(kmin, s_min[w]); kmax = max(kmax, s_max[w]); }
+      if (kmin <= kmax) { atomicMin(&ctl[0], kmin); atomicMax(&ctl[1], kmax); }
+    }
+  }
   if (idx >= P) return;
   radii[idx] = radius_out;
   tiles[idx] = ntiles;
@@ -271,10 +289,22 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   depth_key[idx] = ntiles ? dkey : 0xffffffffu;
 }
 
+// The depth keys as preprocess wrote them (the sort ping-pongs through that array): rebuilt from the records
+// when the depth stage has to be repeated on more key bits.
+__global__ void __launch_bounds__(256)
+depth_keys_kernel(int P, const SplatRecord* __restrict__ rec, const uint32_t* __restrict__ tiles,
+                  uint32_t* __restrict__ depth_key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  depth_key[i] = tiles[i] ? __float_as_uint(rec[i].c.z) : 0xffffffffu;
+}
+
 // emit_rec -> depth order (one 16-byte gather per Gaussian); .y becomes the Gaussian id.
 __global__ void __launch_bounds__(256)
 gather_emit_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* __restrict__ emit_rec,
                    uint4* __restrict__ sorted_emit, uint32_t* __restrict__ sorted_cnt) {
+  pdl_wait();
+  pdl_trigger();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= P) return;
   const uint32_t id = sorted_idx[j];
@@ -314,7 +344,9 @@ __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32_t* __restrict__ sorted_cnt,
                       const uint32_t* __restrict__ offsets, const SplatRecord* __restrict__ rec,
                       const int* __restrict__ radii, uint32_t* __restrict__ tile_keys,
-                      uint32_t* __restrict__ vals, uint32_t gx, uint32_t gy) {
+                      uint32_t* __restrict__ vals, uint32_t gx, uint32_t gy, uint32_t capacity) {
+  pdl_wait();
+  pdl_trigger();
   const unsigned full = 0xffffffffu;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -342,7 +374,7 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
     const uint32_t g_x = __shfl_sync(full, e.x, g), g_id = __shfl_sync(full, e.y, g);
     const uint32_t g_lo = __shfl_sync(full, e.z, g), g_hi = __shfl_sync(full, e.w, g);
     const uint32_t g_rw = g_x >> 22;
-    if (t < end && g_rw) {
+    if (t < end && t < capacity && g_rw) {
       const int bit = kth_set_bit64(g_lo, g_hi, (int)(t - g_off));
       const uint32_t x0 = g_x & 2047u, y0 = (g_x >> 11) & 2047u;
       const uint32_t ty = (uint32_t)bit / g_rw, tx = (uint32_t)bit - ty * g_rw;
@@ -378,8 +410,10 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
       const unsigned bal = __ballot_sync(full, r);
       if (r) {
         const uint32_t pos = o + __popc(bal & ((1u << lane) - 1u));
-        tile_keys[pos] = y * gx + x;
-        vals[pos] = idx;
+        if (pos < capacity) {
+          tile_keys[pos] = y * gx + x;
+          vals[pos] = idx;
+        }
       }
       o += __popc(bal);
     }
@@ -389,7 +423,11 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
 // identifyTileRanges (rasterizer_impl.cu:195-220) on 32-bit tile keys; no pad entries exist.
 // Four consecutive keys per thread (one 16-byte load + the predecessor).
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ tile_keys, uint2* __restrict__ ranges) {
+tile_ranges_kernel(uint32_t L_cap, const uint32_t* __restrict__ L_dev, const uint32_t* __restrict__ tile_keys,
+                   uint2* __restrict__ ranges) {
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t L = L_dev ? min(*L_dev, L_cap) : L_cap;
   const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   if (i0 >= L) return;
   const uint32_t n = min(4u, L - i0);
@@ -428,6 +466,8 @@ tile_order_kernel(uint32_t T, const uint2* __restrict__ ranges, uint32_t* __rest
   const uint32_t tid = threadIdx.x;
   bins[tid] = 0;
   if (tid == 0) smax = 0;
+  pdl_wait();
+  pdl_trigger();
   __syncthreads();
   uint32_t m = 0;
   for (uint32_t t = tid; t < T; t += 1024) m = max(m, ranges[t].y - ranges[t].x);
@@ -551,29 +591,35 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
       prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
       cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
       prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
-      g.emit_rec, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0, prm.raw_inputs != 0);
+      g.emit_rec, g.ctl, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0, prm.raw_inputs != 0);
   return check_launch("preprocess_fwd", prm.debug != 0, s);
 }
 
-int launch_gather_emit(const DgrParams& prm, const GeomState& g, cudaStream_t s) {
-  gather_emit_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_idx, g.emit_rec, g.sorted_emit,
-                                                         g.sorted_cnt);
+int launch_depth_keys(const DgrParams& prm, const GeomState& g, cudaStream_t s) {
+  depth_keys_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.rec, g.tiles, g.depth_key);
+  return check_launch("depth_keys", prm.debug != 0, s);
+}
+
+int launch_gather_emit(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, cudaStream_t s) {
+  launch_pdl(gather_emit_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, sorted_idx,
+             (const uint4*)g.emit_rec, g.sorted_emit, g.sorted_cnt);
   return check_launch("gather_emit", prm.debug != 0, s);
 }
 
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
-                uint32_t* vals, cudaStream_t s) {
+                uint32_t* vals, uint32_t capacity, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
-  emit_instances_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, g.sorted_emit, g.sorted_cnt, g.offsets,
-                                                            g.rec, radii, tile_keys, vals, gx, gy);
+  launch_pdl(emit_instances_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, (const uint4*)g.sorted_emit,
+             (const uint32_t*)g.sorted_cnt, (const uint32_t*)g.offsets, (const SplatRecord*)g.rec, (const int*)radii, tile_keys,
+             vals, gx, gy, capacity);
   return check_launch("emit_instances", prm.debug != 0, s);
 }
 
-int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* tile_keys, uint2* ranges,
-                       cudaStream_t s) {
+int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* R_dev, const uint32_t* tile_keys,
+                       uint2* ranges, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
-  if (R > 0) tile_ranges_kernel<<<(R + 1023) / 1024, 256, 0, s>>>(R, tile_keys, ranges);
+  if (R > 0) launch_pdl(tile_ranges_kernel, dim3((R + 1023) / 1024), dim3(256), 0, s, R, R_dev, tile_keys, ranges);
   return check_launch("tile_ranges", prm.debug != 0, s);
 }
 
@@ -585,7 +631,7 @@ __global__ void tile_identity_kernel(uint32_t T, uint32_t* __restrict__ order) {
 int launch_tile_order(const DgrParams& prm, const ImgState& im, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   static const bool by_length = !(getenv("DOGS_B200_TILE_ORDER") && getenv("DOGS_B200_TILE_ORDER")[0] == '0');
-  if (by_length) tile_order_kernel<<<1, 1024, 0, s>>>(gx * gy, im.ranges, im.tile_order);
+  if (by_length) launch_pdl(tile_order_kernel, dim3(1), dim3(1024), 0, s, gx * gy, (const uint2*)im.ranges, im.tile_order);
   else tile_identity_kernel<<<(gx * gy + 255) / 256, 256, 0, s>>>(gx * gy, im.tile_order);
   return check_launch("tile_order", prm.debug != 0, s);
 }

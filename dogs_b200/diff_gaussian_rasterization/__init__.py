@@ -58,6 +58,27 @@ def cpu_deep_copy_tuple(input_tuple):
     return tuple(i.cpu().clone() if isinstance(i, torch.Tensor) else i for i in input_tuple)
 
 
+# Capacity (in tile instances) handed to dgr_forward as DgrParams::instance_capacity, per device: 1.25x the largest
+# instance count seen so far.  With a capacity the forward is enqueued in one go and the host reads the instance
+# count only after the last launch (no GPU bubble); the first call on a device, and DOGS_B200_SYNC_FORWARD=1,
+# use the exact, synchronising path.  A count above the capacity re-runs the binning stages inside the call.
+_INSTANCE_CAPACITY = {}
+# Likewise DgrParams::depth_key_bits: the largest number of significant depth-key bits seen so far (the depth sort
+# runs one 8-bit pass per 8 of them; the forward verifies the assumption and repeats the stage if it was too low).
+_DEPTH_KEY_BITS = {}
+_SYNC_FORWARD = os.environ.get("DOGS_B200_SYNC_FORWARD", "0") == "1"
+
+
+def _capacity_for(device):
+    return 0 if _SYNC_FORWARD else _INSTANCE_CAPACITY.get(torch.device(device).index or 0, 0)
+
+
+def _learn_capacity(device, info):
+    k = torch.device(device).index or 0
+    _INSTANCE_CAPACITY[k] = max(_INSTANCE_CAPACITY.get(k, 0), int(info.num_rendered * 1.25) + 4096)
+    _DEPTH_KEY_BITS[k] = max(_DEPTH_KEY_BITS.get(k, 0), int(info.depth_key_bits))
+
+
 def _params(rs, P, M, device, backward=False):
     f = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
     keep = (f(rs.bg), f(rs.viewmatrix), f(rs.projmatrix), f(rs.campos))
@@ -163,6 +184,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         num_rendered = 0
         if P != 0:
             prm, keep = _params(rs, P, M, device)
+            prm.instance_capacity = _capacity_for(device)
+            prm.depth_key_bits = _DEPTH_KEY_BITS.get(device.index or 0, 0)
             info = L.DgrForwardInfo()
             with torch.cuda.device(device):
                 args = (C.byref(prm), L.ptr(means3D), L.ptr(dc), L.ptr(sh), L.ptr(colors_precomp),
@@ -181,7 +204,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                         raise ex
                 else:
                     L.check(L.lib().dgr_forward(*args))
-            num_rendered = info.num_rendered
+            num_rendered = info.binning_rows    # the row count the binning buffer is carved with
+            _learn_capacity(device, info)
             scratch.buffers.clear()      # stream-ordered: safe to hand back to the caching allocator now
             del keep
         else:

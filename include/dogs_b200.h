@@ -84,6 +84,19 @@ typedef struct DgrParams {
    * each Gaussian was blended into, important_score[P] = that count times its (anti-aliased) opacity. */
   int32_t* gaussians_count;
   float* important_score;
+  /* forward only.  0: the binning buffers are sized by the instance count R, which the host reads in the middle
+   * of the pass (one stream synchronisation; the reference has two).  > 0: capacity in tile instances — the
+   * buffers are allocated for that many rows up front, the whole pass is enqueued at once with R taken from
+   * device memory, and the host reads R only after everything has been launched, so the GPU never waits for it.
+   * If R turns out larger (nothing is written out of bounds) the stages after the scan are re-run with exactly
+   * sized buffers.  Results are identical either way.  A good value is ~1.25x the largest R seen so far. */
+  int32_t instance_capacity;
+  /* forward only.  Number of low bits of the depth keys (float bits of the view-space depth) the caller expects
+   * to differ between the Gaussians of the frame, 1..32 (0 = 32): positive floats of one scene share their top
+   * bits, and every 8 bits less is one pass of the depth sort less.  Take DgrForwardInfo::depth_key_bits of
+   * earlier frames (their maximum).  The forward verifies it and repeats the depth stage on 32 bits if the
+   * range was wider, so the results never depend on this value. */
+  int32_t depth_key_bits;
 } DgrParams;
 
 /* Sizes / counters reported by dgr_forward (host side). */
@@ -91,6 +104,9 @@ typedef struct DgrForwardInfo {
   int32_t num_rendered;    /* tile instances that survive the per-tile cull (R_valid) */
   int32_t num_visible;     /* Gaussians with radii > 0 and at least one instance (not synced: -1) */
   size_t geom_bytes, binning_bytes, image_bytes, scratch_bytes;
+  int32_t depth_key_bits;  /* bits in which the depth keys of this frame actually differed (see DgrParams) */
+  int32_t binning_rows;    /* rows the binning buffer was carved for (= num_rendered, or the capacity that was used):
+                              pass THIS as `num_rendered` to dgr_backward and dgr_layout */
 } DgrForwardInfo;
 
 /* Forward.  Nullable inputs follow the reference: exactly one of (dc+sh | colors_precomp),
@@ -109,7 +125,8 @@ int dgr_forward(const DgrParams* prm,
                 dogs_alloc_fn scratch_alloc, void* scratch_user,
                 DgrForwardInfo* info, void* stream);
 
-/* Backward.  geom/binning/image are the buffers handed out during dgr_forward.
+/* Backward.  geom/binning/image are the buffers handed out during dgr_forward; num_rendered =
+ * DgrForwardInfo::binning_rows of that forward.
  * Every gradient output is fully written (zeros where the reference relies on
  * torch::zeros, rasterize_points.cu:196-207), so the caller may pass torch.empty.
  * Nullable outputs: dL_ddc/dL_dsh (when colors_precomp was used), dL_dcolors_precomp,

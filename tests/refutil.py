@@ -152,8 +152,10 @@ def ref_forward_raw(dgr, scene, bg=None, antialiasing=False, debug=False):
     return dict(zip(keys, out))
 
 
-def ours_forward_raw(scene, bg=None, antialiasing=False, depth_threshold=0.0, debug=False):
-    """Calls dgr_forward through the C-ABI and returns outputs + parsed state."""
+def ours_forward_raw(scene, bg=None, antialiasing=False, depth_threshold=0.0, debug=False, instance_capacity=0,
+                     depth_key_bits=0):
+    """Calls dgr_forward through the C-ABI and returns outputs + parsed state.  instance_capacity > 0 selects
+    the path that enqueues the whole pass before the host knows the instance count."""
     from dogs_b200 import _lib as L
     from dogs_b200.diff_gaussian_rasterization import _params, GaussianRasterizationSettings
     dev = scene["means3D"].device
@@ -165,6 +167,8 @@ def ours_forward_raw(scene, bg=None, antialiasing=False, depth_threshold=0.0, de
                                        scene["campos"], False, debug, antialiasing, depth_threshold)
     M = scene["sh"].shape[1]
     prm, keep = _params(rs, P, M, dev)
+    prm.instance_capacity = int(instance_capacity)
+    prm.depth_key_bits = int(depth_key_bits)
     color = torch.empty(3, H, W, device=dev)
     invdepth = torch.empty(1, H, W, device=dev)
     radii = torch.empty(P, dtype=torch.int32, device=dev)
@@ -179,12 +183,12 @@ def ours_forward_raw(scene, bg=None, antialiasing=False, depth_threshold=0.0, de
     torch.cuda.synchronize()
     R = info.num_rendered
     lay = L.DgrLayout()
-    L.check(L.lib().dgr_layout(P, W, H, R, C.byref(lay)))
+    L.check(L.lib().dgr_layout(P, W, H, info.binning_rows, C.byref(lay)))
     g, b, im = al[0].last, al[1].last, al[2].last
     N = H * W
     T = ((W + 15) // 16) * ((H + 15) // 16)
     rec = g[lay.geom_record:lay.geom_record + 48 * P].view(torch.float32).view(P, 12)
-    out = dict(num_rendered=R, color=color, invdepth=invdepth, radii=radii,
+    out = dict(num_rendered=R, binning_rows=info.binning_rows, depth_key_bits=info.depth_key_bits, color=color, invdepth=invdepth, radii=radii,
                conic_opacity=rec[:, 0:4], means2D=rec[:, 4:6], invdepths=rec[:, 6],
                rgb=torch.stack([rec[:, 7], rec[:, 8], rec[:, 9]], 1), depths=rec[:, 10],
                clamped=g[lay.geom_clamped:lay.geom_clamped + P],

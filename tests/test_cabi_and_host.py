@@ -35,7 +35,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from dogs_b200 import _lib
     # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 2 ints, 1 pointer, 2 pointers
-    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16
+    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16 + 8       # + instance_capacity, padded
+    assert _lib.DgrParams.instance_capacity.offset == 112 and _lib.DgrParams.depth_key_bits.offset == 116
+    assert _lib.DgrForwardInfo.depth_key_bits.offset == 40 and _lib.DgrForwardInfo.binning_rows.offset == 44
     assert _lib.DgrParams.bg.offset == 48 and _lib.DgrParams.ref_bucket_cull_quirk.offset == 80
     assert _lib.DgrParams.raw_inputs.offset == 84 and _lib.DgrParams.admm.offset == 88
     assert C.sizeof(_lib.DgrAdmmPenalty) == 6 * 8 + 6 * 4 + 8

@@ -408,3 +408,48 @@ def test_full_size_properties(cfg):
     g2 = U.ours_backward(sc, 2.0 * dLc, 2.0 * dLd)
     for k in ("dc", "opacities", "means2D"):
         assert U.rel_to_max(g2[k], 2.0 * g1[k]) <= 1e-5, k            # backward is linear in dL/dout
+
+
+@pytest.mark.parametrize("cfg,P", [("tiny", None), ("tiny", 1), ("C1", None)])
+def test_forward_without_host_round_trip_is_identical(cfg, P):
+    """DgrParams::instance_capacity: the pass enqueued in one go with the instance count taken from device memory
+    (capacity >= R), and the re-run when the count exceeds the capacity (capacity < R), against the exact path."""
+    sc = scenes.make_scene(cfg, 8, DEV, P=P)
+    a = U.ours_forward_raw(sc)
+    R = a["num_rendered"]
+    assert a["binning_rows"] == R
+    kb = a["depth_key_bits"]
+    assert 1 <= kb <= 32
+    # the depth sort on the expected number of key bits: exact (kb), too many (32), too few (the stage is repeated)
+    for cap, bits in ((R + 1000, 0), (max(R, 1), kb), (max(R // 3, 1), kb), (1, 32), (R + 5, max(kb - 9, 1)), (0, max(kb - 9, 1)),
+                      (0, 1)):
+        o = U.ours_forward_raw(sc, instance_capacity=cap, depth_key_bits=bits)
+        assert o["num_rendered"] == R and o["depth_key_bits"] == kb
+        assert o["binning_rows"] == (cap if cap >= R and not (0 < bits < kb) else R)
+        for k in ("color", "invdepth", "radii", "n_contrib", "ranges", "point_list", "tile_keys"):
+            assert torch.equal(o[k], a[k]), (cap, bits, k)
+        assert torch.equal(U.bits(o["final_T"]), U.bits(a["final_T"]))
+    # through the public API: the first call on a device learns the capacity, the following ones use it
+    import dogs_b200.diff_gaussian_rasterization as mine
+    dLc, dLd = _out_grads(sc)
+    saved, saved_bits = dict(mine._INSTANCE_CAPACITY), dict(mine._DEPTH_KEY_BITS)
+    try:
+        grads = []
+        for mode in ("sync", "learn", "capacity", "too_small"):
+            if mode == "sync":
+                mine._INSTANCE_CAPACITY.clear()
+                mine._DEPTH_KEY_BITS.clear()
+            if mode == "too_small":
+                mine._INSTANCE_CAPACITY[0] = max(R // 2, 1)
+                mine._DEPTH_KEY_BITS[0] = 3
+            grads.append(U.ours_backward(sc, dLc, dLd))
+            if mode != "sync":
+                assert mine._INSTANCE_CAPACITY[0] >= R and mine._DEPTH_KEY_BITS[0] >= kb
+        for g in grads[1:]:
+            for k in ("dc", "opacities", "means2D"):
+                assert U.rel_to_max(g[k], grads[0][k]) <= 1e-6, k
+    finally:
+        mine._INSTANCE_CAPACITY.clear()
+        mine._INSTANCE_CAPACITY.update(saved)
+        mine._DEPTH_KEY_BITS.clear()
+        mine._DEPTH_KEY_BITS.update(saved_bits)
