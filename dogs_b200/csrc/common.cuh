@@ -186,6 +186,43 @@ template <typename K> static void allow_big_smem(K kernel, bool (&done)[64]) {
   }
 }
 
+// ---- bulk asynchronous copies (TMA engine, 1-D: cp.async.bulk; SASS UBLKCP) + mbarrier ------------------------
+// One elected thread moves a contiguous block between global and shared memory without LSU instructions or
+// registers; completion of a load is signalled on an mbarrier (complete_tx byte count), so the rest of the CTA
+// computes while the block is in flight.  Addresses and sizes must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arm the barrier with the byte count of the copy and start it
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra MBAR_WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (call in the writing threads, then barrier)
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global; returns when the shared source may be reused (and the CTA may exit)
+__device__ __forceinline__ void bulk_store_and_wait(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- programmatic dependent launch ----------------------------------------------------------------------------
 // The rasterizer is a chain of ~30 short kernels per step, each depending on the previous one.  Launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, a kernel may be scheduled while its predecessor is still

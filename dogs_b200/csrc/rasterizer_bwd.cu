@@ -296,21 +296,27 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drots,
                       float* __restrict__ dL_dcov3D_out, const DgrAdmmPenalty admm, bool raw_inputs,
                       double* __restrict__ pen_partial) {
-  extern __shared__ float4 stage4[];
+  extern __shared__ __align__(128) float4 stage4[];
   float* stage = reinterpret_cast<float*>(stage4);
+  __shared__ __align__(8) uint64_t sh_bar;
   const int first = blockIdx.x * PREB_THREADS;
   const int idx = first + threadIdx.x;
   const int count = min(PREB_THREADS, P - first);
   const bool sh_path = (dL_dsh != nullptr) && M > 0;
   const size_t nfl = (size_t)count * 3 * M;
+  // The CTA's SH slice arrives as one bulk copy (TMA engine) while the threads run the covariance chain; the
+  // gradient slice that replaces it in shared memory leaves the same way.  Fallback (slice not a multiple of
+  // 16 bytes, misaligned tensor): coalesced LSU loads / stores.
+  bool bulk = false;
   if (sh_path) {
     if (D > 0) {
       const float* src = shs + (size_t)first * 3 * M;
-      if ((((uintptr_t)src) & 15) == 0) {
-        const float4* src4 = reinterpret_cast<const float4*>(src);
-        const size_t n4 = nfl >> 2;
-        for (size_t i = threadIdx.x; i < n4; i += PREB_THREADS) stage4[i] = __ldg(src4 + i);
-        for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) stage[i] = __ldg(src + i);
+      bulk = (((uintptr_t)src) & 15) == 0 && ((nfl * sizeof(float)) & 15) == 0;
+      if (bulk) {
+        if (threadIdx.x == 0) {
+          mbar_init(&sh_bar, 1);
+          bulk_load(stage, src, (uint32_t)(nfl * sizeof(float)), &sh_bar);
+        }
       } else {
         for (size_t i = threadIdx.x; i < nfl; i += PREB_THREADS) stage[i] = __ldg(src + i);
       }
@@ -331,8 +337,10 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     float g_cov3D[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool visible = radii[idx] > 0;
     if (!visible) {
-      if (sh_path)
+      if (sh_path) {
+        if (bulk) mbar_wait(&sh_bar, 0);     // the incoming copy must not land on top of the zeros
         for (int i = 0; i < 3 * M; i++) sh_row[i] = 0.f;
+      }
     } else {
       const float4* acc4 = reinterpret_cast<const float4*>(accum + (size_t)idx * ACC_STRIDE);
       const float4 A0 = acc4[0], A1 = acc4[1], A2 = acc4[2];
@@ -366,6 +374,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       g_mean3D.z += (proj[8] * m_w - proj[11] * mul1) * dL_dmean2D.x + (proj[9] * m_w - proj[11] * mul2) * dL_dmean2D.y;
 
       if (sh_path) {
+        if (bulk) mbar_wait(&sh_bar, 0);
         V3 pos = {mean.x, mean.y, mean.z};
         V3 cp = {campos[0], campos[1], campos[2]};
         V3 dLc = {g_color[0], g_color[1], g_color[2]};
@@ -449,9 +458,15 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   }
 
   if (sh_path) {
-    __syncthreads();
+    if (bulk) mbar_wait(&sh_bar, 0);       // threads beyond P: nobody passes while the copy may still be in flight
     float* dst = dL_dsh + (size_t)first * 3 * M;
     const bool pen = admm.zmu_sh != nullptr;
+    const bool bulk_out = !pen && (((uintptr_t)dst) & 15) == 0 && ((nfl * sizeof(float)) & 15) == 0;
+    if (bulk_out) fence_smem_to_async();
+    __syncthreads();
+    if (bulk_out) {
+      if (threadIdx.x == 0) bulk_store_and_wait(dst, stage, (uint32_t)(nfl * sizeof(float)));
+    } else {
     const float* xs = shs + (size_t)first * 3 * M;            // still L2-resident: this CTA just read it
     const float* zs = pen ? admm.zmu_sh + (size_t)first * 3 * M : nullptr;
     const bool al16 = ((((uintptr_t)dst) | ((uintptr_t)xs) | ((uintptr_t)zs)) & 15) == 0;
@@ -480,6 +495,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         if (pen) { const float r = xs[i] - zs[i]; g += admm.coef_sh * r; pen_sh += (double)(r * r); }
         dst[i] = g;
       }
+    }
     }
   }
   if (pen_partial) {

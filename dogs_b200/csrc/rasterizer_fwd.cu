@@ -108,24 +108,31 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       uint32_t* __restrict__ depth_key, uint4* __restrict__ emit_rec,
                       uint32_t* __restrict__ ctl,
                       uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing, bool raw_inputs) {
-  extern __shared__ float4 sh_stage4[];
+  extern __shared__ __align__(128) float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
+  __shared__ __align__(8) uint64_t sh_bar;
   const int first = blockIdx.x * PRE_THREADS;
   const int idx = first + threadIdx.x;
   const bool use_sh = (colors_precomp == nullptr) && D > 0 && M > 0;
+  // The CTA's SH slice (count * 3M floats, contiguous) goes to shared memory as ONE bulk copy issued by one
+  // thread; it lands while the threads project their Gaussians and build the covariances, and is awaited
+  // (mbarrier) only where the colours are evaluated.  Fallback for a slice that is not a multiple of 16 bytes
+  // (ragged last CTA) or a misaligned tensor: coalesced loads through the LSU.
+  bool bulk = false;
   if (use_sh) {
     const int count = min(PRE_THREADS, P - first);
     const size_t nfl = (size_t)count * 3 * M;
     const float* src = shs + (size_t)first * 3 * M;
-    if ((((uintptr_t)src) & 15) == 0) {
-      const float4* src4 = reinterpret_cast<const float4*>(src);
-      const size_t n4 = nfl >> 2;
-      for (size_t i = threadIdx.x; i < n4; i += PRE_THREADS) sh_stage4[i] = __ldg(src4 + i);
-      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PRE_THREADS) sh_stage[i] = __ldg(src + i);
+    bulk = (((uintptr_t)src) & 15) == 0 && ((nfl * sizeof(float)) & 15) == 0;
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        mbar_init(&sh_bar, 1);
+        bulk_load(sh_stage, src, (uint32_t)(nfl * sizeof(float)), &sh_bar);
+      }
     } else {
       for (size_t i = threadIdx.x; i < nfl; i += PRE_THREADS) sh_stage[i] = __ldg(src + i);
     }
-    __syncthreads();
+    __syncthreads();     // the barrier is initialised (bulk) / the slice is staged (fallback)
   }
   // (no early return: the whole warp meets again for the cooperative rect walk below)
 
@@ -192,6 +199,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       V3 pos = {p_orig.x, p_orig.y, p_orig.z};
       V3 cp = {cam_pos[0], cam_pos[1], cam_pos[2]};
       V3 d0 = {dc[3 * idx], dc[3 * idx + 1], dc[3 * idx + 2]};
+      if (bulk) mbar_wait(&sh_bar, 0);
       V3 c = color_from_sh(D, pos, cp, d0, sh_stage + (size_t)threadIdx.x * 3 * M, clamped);
       rgb = {c.x, c.y, c.z};
     } else {
@@ -282,6 +290,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       if (kmin <= kmax) { atomicMin(&ctl[0], kmin); atomicMax(&ctl[1], kmax); }
     }
   }
+  if (bulk) mbar_wait(&sh_bar, 0);     // nobody leaves while the copy may still be writing this CTA's shared memory
   if (idx >= P) return;
   radii[idx] = radius_out;
   tiles[idx] = ntiles;
