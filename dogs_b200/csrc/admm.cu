@@ -158,14 +158,19 @@ struct ConsensusArgs {
 //   zmu = z - u for the per-iteration penalty.  Residual sums in FP64: partial[blk][g] = sum (z - x)^2
 //   (primal, master:396-432), partial[blk][6+g] = sum (z_prev - z)^2 / count (dual, master:435-456: every
 //   global Gaussian once); the last CTA to finish folds the partials in a fixed order into residuals[12].
+// MAXA > 0: at most MAXA addends per row, all table entries and all addend rows are fetched before anything is
+// summed (independent loads in flight instead of an entry -> row -> entry -> row chain); MAXA = 0: any number.
+template <int MAXA>
 __global__ void __launch_bounds__(ADMM_THREADS)
 admm_consensus_kernel(const __grid_constant__ ConsensusArgs a, const int32_t* __restrict__ shared_row,
                       const uint32_t* __restrict__ addends, const uint8_t* __restrict__ count, int max_addends,
                       int64_t n, float relax, double* __restrict__ partial, unsigned int* __restrict__ ticket,
                       double* __restrict__ residuals) {
   __shared__ double acc[12];
+  __shared__ double inv_cnt[ADMM_THREADS];     // 1 / count without a double division per element
   __shared__ bool last;
   if (threadIdx.x < 12) acc[threadIdx.x] = 0.0;
+  inv_cnt[threadIdx.x] = 1.0 / (double)max((int)threadIdx.x, 1);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const RowLane rl = row_lane(lane);
@@ -174,36 +179,70 @@ admm_consensus_kernel(const __grid_constant__ ConsensusArgs a, const int32_t* __
   const int64_t nwarps = (int64_t)gridDim.x * (ADMM_THREADS / 32);
   for (int64_t i = (int64_t)blockIdx.x * (ADMM_THREADS / 32) + (threadIdx.x >> 5); i < n; i += nwarps) {
     const int32_t sr = shared_row[i];
-    float cnt = 1.f;
-    if (sr >= 0) cnt = (float)count[sr];
+    int cnt_i = 1;
+    uint32_t ent[MAXA > 0 ? MAXA : 1];
+    if (sr >= 0) {
+      cnt_i = count[sr];
+      if (MAXA > 0) {
+#pragma unroll
+        for (int j = 0; j < MAXA; j++) ent[j] = j < max_addends ? addends[(int64_t)sr * max_addends + j] : 0xffffffffu;
+      }
+    }
+    const float cnt = (float)cnt_i;
+    const double w = inv_cnt[cnt_i];
+    float xv[2], z_old[2], u_val[2], add[2][MAXA > 0 ? MAXA : 1];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (rl.g[h] < 0) continue;
+      const int64_t e = i * rl.sz[h] + rl.off[h];
+      xv[h] = a.x[rl.g[h]][e];
+      z_old[h] = a.z[rl.g[h]][e];
+      u_val[h] = a.u[rl.g[h]][e];
+      if (MAXA > 0 && sr >= 0) {
+#pragma unroll
+        for (int j = 0; j < MAXA; j++) {
+          const uint32_t which = ent[j] >> 28;
+          add[h][j] = (ent[j] == 0xffffffffu || which == 15u)
+                          ? 0.f
+                          : __ldg(a.src[which] + (int64_t)(ent[j] & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       if (rl.g[h] < 0) continue;
       const int g = rl.g[h];
       const int64_t e = i * rl.sz[h] + rl.off[h];
-      const float xv = a.x[g][e];
-      const float z_old = a.z[g][e];
-      float u_new = a.u[g][e];
-      float z_new = xv;
+      float u_new = u_val[h];
+      float z_new = xv[h];
       if (sr >= 0) {
         float s = 0.f;
-        for (int j = 0; j < max_addends; j++) {
-          const uint32_t ent = addends[(int64_t)sr * max_addends + j];
-          if (ent == 0xffffffffu) break;
-          const uint32_t which = ent >> 28;
-          const float v = which == 15u ? xv
-                                       : __ldg(a.src[which] + (int64_t)(ent & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
-          s = j == 0 ? v : __fadd_rn(s, v);
+        if (MAXA > 0) {
+#pragma unroll
+          for (int j = 0; j < MAXA; j++) {
+            if (ent[j] == 0xffffffffu) break;
+            const float v = (ent[j] >> 28) == 15u ? xv[h] : add[h][j];
+            s = j == 0 ? v : __fadd_rn(s, v);
+          }
+        } else {
+          for (int j = 0; j < max_addends; j++) {
+            const uint32_t en = addends[(int64_t)sr * max_addends + j];
+            if (en == 0xffffffffu) break;
+            const uint32_t which = en >> 28;
+            const float v = which == 15u ? xv[h]
+                                         : __ldg(a.src[which] + (int64_t)(en & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
+            s = j == 0 ? v : __fadd_rn(s, v);
+          }
         }
         z_new = __fdiv_rn(s, cnt);
-        u_new = __fadd_rn(u_new, __fmul_rn(relax, __fsub_rn(xv, z_new)));
+        u_new = __fadd_rn(u_new, __fmul_rn(relax, __fsub_rn(xv[h], z_new)));
         a.u[g][e] = u_new;
       }
       a.z[g][e] = z_new;
       if (has_zmu) a.zmu[g][e] = z_new - u_new;
-      const double dp = (double)z_new - (double)xv, dd = (double)z_old - (double)z_new;
+      const double dp = (double)z_new - (double)xv[h], dd = (double)z_old[h] - (double)z_new;
       primal[h] += dp * dp;
-      dual[h] += dd * dd / (double)cnt;
+      dual[h] += dd * dd * w;
     }
   }
 #pragma unroll
@@ -279,8 +318,12 @@ extern "C" int admm_consensus_update(const AdmmConstTensors* x, const AdmmTensor
   for (int k = 0; k < ADMM_MAX_SOURCES; k++) a.src[k] = (sources && k < n_sources) ? sources[k] : nullptr;
   double* partial = reinterpret_cast<double*>(scratch);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(scratch) + (size_t)(148 * 8) * 12 * sizeof(double));
-  admm_consensus_kernel<<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
-                                                                  relax, partial, ticket, residuals);
+  if (max_addends <= 4)
+    admm_consensus_kernel<4><<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
+                                                                       relax, partial, ticket, residuals);
+  else
+    admm_consensus_kernel<0><<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
+                                                                       relax, partial, ticket, residuals);
   return check_launch("admm_consensus_update", false, s);
 }
 

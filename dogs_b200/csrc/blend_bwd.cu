@@ -84,7 +84,7 @@ __device__ __forceinline__ int bb_slot(int lane) {
 // HAS_DEPTH = false: no gradient arrives through the inverse-depth image (the usual photometric loss),
 // so the depth terms are compiled out (they would only add exact zeros).
 template <bool HAS_DEPTH>
-__global__ void __launch_bounds__(BB_THREADS)
+__global__ void __launch_bounds__(BB_THREADS, 12)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                  const uint32_t* __restrict__ point_list, int W,
                  int H, const float* __restrict__ bg_color, const SplatRecord* __restrict__ rec,
@@ -117,16 +117,17 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const float bg0 = bg_color[0], bg1 = bg_color[1], bg2 = bg_color[2];
 
   // per-pixel state (k = 8x4 block index, top to bottom)
+  // (the four pixels of a thread share their x; y = pyf0 + 4k.  S carries the background term as well:
+  //  dL/dalpha = cd*T + (S - T_final * bg.dL/dC) / (1 - alpha), and the subtrahend is constant per pixel)
   uint32_t last[4];
-  float T[4], S[4], dC0[4], dC1[4], dC2[4], dD[4], bgT[4], pxf[4], pyf[4];
+  float T[4], S[4], dC0[4], dC1[4], dC2[4], dD[4];
+  const float pxf = (float)qx, pyf0 = (float)qy;
   uint32_t lmax = 0, lmax01 = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const uint32_t px = qx, py = qy + 4 * k;
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-    pxf[k] = (float)px;
-    pyf[k] = (float)py;
-    last[k] = 0; T[k] = 1.0f; S[k] = 0.f; dC0[k] = dC1[k] = dC2[k] = dD[k] = 0.f; bgT[k] = 0.f;
+    last[k] = 0; T[k] = 1.0f; S[k] = 0.f; dC0[k] = dC1[k] = dC2[k] = dD[k] = 0.f;
     if (inside) {
       const uint32_t pix_id = W * py + px;
       last[k] = n_contrib[pix_id];
@@ -138,7 +139,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       S[k] = -(pixel_colors[0 * HW + pix_id] * dC0[k] + pixel_colors[1 * HW + pix_id] * dC1[k] +
                pixel_colors[2 * HW + pix_id] * dC2[k] + (HAS_DEPTH ? pixel_invdepths[pix_id] * dD[k] : 0.f));
       // backward.cu:604-621: the background term (-T_final/(1-alpha)) * (bg . dL/dC)
-      bgT[k] = final_Ts[pix_id] * (bg0 * dC0[k] + bg1 * dC1[k] + bg2 * dC2[k]);
+      S[k] -= final_Ts[pix_id] * (bg0 * dC0[k] + bg1 * dC1[k] + bg2 * dC2[k]);
     }
     lmax = max(lmax, last[k]);
     // rows 0-1 of the tile = the first warp of the reference's 16x16 forward block
@@ -206,6 +207,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     // Sub-tile culling (blend_common.cuh): which entries of the batch can reach each of the four 8x4
     // blocks of this warp's half tile; one entry per lane and round, 4 mask bits per entry.
+    // (Measured alternative: four ballots per slice instead of the per-entry shuffle below, so that the
+    // per-block skip becomes a branch on warp-uniform words: 1.28 -> 1.36 ms, dropped.)
     uint32_t hm[2], bm[2];
 #pragma unroll
     for (int w = 0; w < 2; w++) {
@@ -238,7 +241,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const float4 b = sB[buf][j];
       const float4 cc = sC[buf][j];
       const float invd = b.z;
-      const float dx = b.x - pxf[0];
+      const float dx = b.x - pxf;
       float v[10];
 #pragma unroll
       for (int q = 0; q < 10; q++) v[q] = 0.f;
@@ -250,7 +253,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         // decisions and T are those of the forward pass bit for bit.  (A fast ex2.approx exp was
         // measured: 10 % faster, but the 1e-6 relative change of G decorrelates ill-conditioned conic
         // gradients from the reference's by up to 5e-4 of the tensor max, outside the 1e-4 parity bar.)
-        const float dy = b.y - pyf[k];
+        const float dy = b.y - (pyf0 + 4.f * k);
         const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
         const float G = exp(power);
         const float al = min(0.99f, con_o.w * G);
@@ -267,7 +270,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float om = 1.0f - alpha;
         const float inv = __fdividef(1.0f, om);   // MUFU.RCP (<= 1 ulp): gradients carry a 1e-4 bar
         S[k] += weight * cd;
-        const float dL_dalpha = c ? (cd * Tk + inv * (S[k] - bgT[k])) : 0.f;
+        const float dL_dalpha = c ? (cd * Tk + inv * S[k]) : 0.f;
         T[k] = Tk * om;
         v[6] += weight * dC0[k];
         v[7] += weight * dC1[k];
