@@ -198,7 +198,7 @@ def to_raw(sc):
 class Trainee:
     """One model (scene block): leaf parameters in the model's own shapes, one training step on them."""
 
-    def __init__(self, dgr, loss_of, sc, target, raw=False, admm_block=None, depth_threshold=0.0):
+    def __init__(self, dgr, loss_of, sc, target, raw=False, admm_block=None, depth_threshold=0.0, optimizer=False):
         from dogs_b200 import scenes
         self.scenes, self.dgr, self.loss_of = scenes, dgr, loss_of
         self.sc, self.target = sc, target
@@ -216,6 +216,14 @@ class Trainee:
         if depth_threshold:
             self.kw["depth_threshold"] = depth_threshold
         self.blk = admm_block
+        # SparseGaussianAdam over the six tensors, step(radii > 0, P) as at gaussian_trainer.py:474-476.  The
+        # learning rates are 0: the update runs in full (moments and parameters are read and written) but the scene
+        # stays the seeded one — against a random target image real rates inflate the Gaussians within a few steps
+        # and every later step renders a different, much heavier scene.
+        self.opt = None
+        if optimizer:
+            self.opt = dgr.SparseGaussianAdam([{"params": [self.leaves[k]], "lr": 0.0, "name": k} for k in PARAM_KEYS],
+                                              lr=0.0, eps=1e-15)
 
     def x(self):
         return [self.leaves[k] for k in PARAM_KEYS]
@@ -229,11 +237,13 @@ class Trainee:
         for v in lv.values():
             v.grad = None
         views = dict(lv, dc=lv["dc"].view(self.P, 1, 3), sh=lv["sh"].view(self.P, 15, 3))
-        img, _, _, _ = self.scenes.render(self.dgr, self.sc if scene is None else scene, views, **self.kw)
+        img, radii, _, _ = self.scenes.render(self.dgr, self.sc if scene is None else scene, views, **self.kw)
         loss = self.loss_of(img, self.target if target is None else target)
         loss.backward()
         if self.blk is not None:
             self.blk.add_penalty_grads_()
+        if self.opt is not None:
+            self.opt.step(radii > 0, self.P)
         return loss
 
 
@@ -580,6 +590,17 @@ def main():
                        "gaussians": s2["means3D"].shape[0], "image": [s2["W"], s2["H"]]}
             del m2, s2, t2
         extra["configs"] = cfgs
+        # the same C3 step followed by the sparse Adam update of all six tensors (SURVEY.md 8f.1,
+        # gaussian_trainer.py:474-476): six adamUpdate launches in the reference, one here
+        mo = Trainee(dgr, loss_of, sc, target, optimizer=True)
+        for _ in range(Wm):
+            mo.step()
+        e0, e1, mk = timed_steps(mo.step, K, barrier)
+        barrier()
+        extra["with_optimizer"] = {"value": K / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / K,
+                                   "workload": f"{args.cfg} step + SparseGaussianAdam.step(radii > 0) over the six parameter tensors"}
+        del mo
+        torch.cuda.empty_cache()
         if ours:
             m3, b3 = make_admm_trainee()
             for _ in range(Wm):

@@ -91,14 +91,14 @@ sparse_adam_multi_kernel(const __grid_constant__ AdamMultiArgs a, const uint8_t*
   for (int q = 0; q < ADAM_MAX_TENSORS - 1; q++) t += (q < a.n - 1 && c >= a.chunk_end[q]) ? 1 : 0;
   const unsigned long long lc = c - (t ? a.chunk_end[t - 1] : 0ull);
   const uint32_t M = a.M[t];
-  const unsigned long long len = (unsigned long long)N * M;
-  const unsigned long long e0 = lc * 4;
-  const uint32_t cnt = (uint32_t)min(4ull, len - e0);
-  const uint32_t g0 = (uint32_t)(e0 / M), g3 = (uint32_t)((e0 + cnt - 1) / M);
+  const uint32_t len = N * M;                       // < 2^32 per tensor (checked by the host)
+  const uint32_t e0 = (uint32_t)lc * 4u;
+  const uint32_t cnt = min(4u, len - e0);
+  const uint32_t g0 = e0 / M, g3 = (e0 + cnt - 1) / M;
   bool vis[4] = {false, false, false, false};
   bool any = false;
   for (uint32_t k = 0; k < cnt; k++) {
-    const uint32_t g = (g0 == g3) ? g0 : (uint32_t)((e0 + k) / M);
+    const uint32_t g = (g0 == g3) ? g0 : (e0 + k) / M;
     vis[k] = radii ? radii[g] > 0 : visible[g] != 0;
     any |= vis[k];
   }
@@ -151,6 +151,7 @@ extern "C" int dgr_sparse_adam_multi(const DgrAdamTensor* tensors, int32_t n_ten
     }
     a.param[t] = x.param; a.grad[t] = x.grad; a.exp_avg[t] = x.exp_avg; a.exp_avg_sq[t] = x.exp_avg_sq;
     a.M[t] = x.M; a.lr[t] = x.lr; a.eps[t] = x.eps;
+    if ((unsigned long long)N * x.M > 0xffffffffull) { set_error("sparse_adam_multi: tensor %d too large", t); return 1; }
     end += ((unsigned long long)N * x.M + 3) / 4;
     a.chunk_end[t] = end;
   }
