@@ -312,6 +312,20 @@ def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed):
     for b in mine:
         models[b].attach(grp.blocks[b].fuse_into_rasterizer(True, all_groups=True))
     del xyz
+    check = None
+    if distributed:
+        # untimed self-check of the transport: the same round through batched NCCL send/recv must give the same z
+        ref = A.ConsensusGroup({b: [t.detach().clone() for t in models[b].x()] for b in mine}, topo, p2p=False)
+        chk = A.ConsensusGroup({b: [t.detach().clone() for t in models[b].x()] for b in mine}, topo)
+        ref.consensus(adapt=False)
+        chk.consensus(adapt=False)
+        dz = torch.stack([(p_ - q_).abs().max() for b in mine for p_, q_ in zip(ref.blocks[b].z, chk.blocks[b].z)]).max()
+        dist.all_reduce(dz, op=dist.ReduceOp.MAX)
+        check = {"transport": ("peer memory: the pack kernel writes the co-owners' receive buffers (torch symmetric memory)"
+                               if chk.p2p is not None else "NCCL send/recv"),
+                 "peer_memory_error": chk.p2p_error, "max_abs_dz_vs_nccl_send_recv": float(dz.item())}
+        del ref, chk
+        torch.cuda.empty_cache()
 
     def iteration():
         for b in mine:
@@ -355,7 +369,8 @@ def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed):
            "iters_per_s_at_interval_200": 1e3 / (it_ms[K // 2] + round_ms / 200.0),
            "shared_rows_rank0": shared, "exchange_bytes_rank0": {"send_buffer": int(topo.send_rows_total) * 236,
                                                                  "recv_buffer": int(topo.recv_rows_total) * 236},
-           "hbm_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9}
+           "hbm_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9,
+           "exchange": check if check is not None else {"transport": "none: all blocks on one GPU read each other's send rows in place"}}
     del grp, models
     torch.cuda.empty_cache()
     return out

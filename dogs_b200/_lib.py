@@ -92,6 +92,7 @@ SIGNATURES = {
     "sknn_dist2": [C.c_int32, _P, _P, ALLOC_FN, _P, _P],
     "admm_block_membership": [C.c_int64, _P, _P, C.c_int32, _P, _P, _P, _P],
     "admm_pack_rows": [C.POINTER(AdmmTensors), _P, C.c_int64, _P, _P],
+    "admm_pack_rows_to": [C.POINTER(AdmmTensors), _P, _P, _P, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, _P],
     "admm_consensus_update": [C.POINTER(AdmmTensors)] * 3 + [_P, _P, _P, _P, C.c_int32, C.c_int64,
                                                              C.POINTER(C.c_void_p), C.c_int32, C.c_float, _P, _P, _P],
     "admm_consensus_scratch_bytes": [],

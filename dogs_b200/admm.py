@@ -23,6 +23,7 @@ The device kernels live in csrc/admm.cu (C-ABI: admm_pack_rows / admm_consensus_
 library and raise if it is missing.
 """
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -58,9 +59,12 @@ class BlockPlan:
         self.send_rows = 0
         self.sends = []             # [(dest rank, first row, rows)] contiguous regions of the send buffer
         self.peers = []             # co-owning block ids (diagnostics)
+        self.messages = []          # [(dest block, dest rank, first row in the send buffer, rows)] in pack order
+        self.p2p_sel = None         # peer-memory exchange: uint8 [R_a] destination buffer of every packed row
+        self.p2p_row = None         #                       int32 [R_a] row in that buffer
 
     def to(self, device):
-        for k in ("shared_row", "addends", "count", "pack_src", "pack_dst"):
+        for k in ("shared_row", "addends", "count", "pack_src", "pack_dst", "p2p_sel", "p2p_row"):
             if getattr(self, k) is not None:
                 setattr(self, k, getattr(self, k).to(device))
         return self
@@ -80,6 +84,7 @@ class Topology:
         self.exchange = "neighbour"
         self.S_total = 0            # dense mode: rows of the all-reduced buffer
         self.group = None
+        self.msg_recv = {}          # (sender block, receiver block) -> first row in THIS rank's receive buffer
 
     def to(self, device):
         for p in self.plans.values():
@@ -224,6 +229,7 @@ def build_topology(local_blocks: Dict[int, torch.Tensor], n_global: int, group=N
                 if ra is None:
                     continue
                 msg_send[(a, b)] = row
+                plan.messages.append((b, r, row, int(ra.numel())))
                 srcs.append(ra)
                 row += ra.numel()
                 plan.peers.append(b)
@@ -253,6 +259,7 @@ def build_topology(local_blocks: Dict[int, torch.Tensor], n_global: int, group=N
             if row > first:
                 topo.recvs.append((r, first, row - first))
     topo.recv_rows_total = row
+    topo.msg_recv = dict(msg_recv)
     if max(topo.send_rows_total, topo.recv_rows_total) >= (1 << 28):
         raise ValueError("exchange buffer exceeds 2^28 rows")
 
@@ -335,6 +342,18 @@ class CudaOps:
         with torch.cuda.device(dev):
             self.L.check(self.lib.admm_pack_rows(C.byref(xs), plan.pack_src.data_ptr(), plan.pack_src.numel(),
                                                  out_rows.data_ptr(), self.L.stream_ptr(dev)))
+
+    def pack_rows_to(self, x, plan, dst_ptrs):
+        """Rows straight into the buffers their consumers read (own send buffer / peers' receive buffers)."""
+        if plan.send_rows == 0:
+            return
+        xs = self._t6(x)
+        dev = plan.pack_src.device
+        arr = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+        with torch.cuda.device(dev):
+            self.L.check(self.lib.admm_pack_rows_to(C.byref(xs), plan.pack_src.data_ptr(), plan.p2p_sel.data_ptr(),
+                                                    plan.p2p_row.data_ptr(), plan.pack_src.numel(), arr, len(dst_ptrs),
+                                                    self.L.stream_ptr(dev)))
 
     def consensus_update(self, x, u, z, zmu, plan, sources, relax, scratch, residuals):
         xs, us, zs = self._t6(x), self._t6(u), self._t6(z)
@@ -507,7 +526,7 @@ class ConsensusGroup:
 
     def __init__(self, blocks: Dict[int, object], topo: Topology, alphas: Sequence[float] = DEFAULT_ALPHAS,
                  over_relaxation_coeff: float = 0.5, mu: float = 10.0, tau_inc: float = 2.0, tau_dec: float = 2.0,
-                 ops=None):
+                 ops=None, p2p: Optional[bool] = None):
         self.topo = topo
         self.group = topo.group
         self.ops = ops if ops is not None else CudaOps()
@@ -528,11 +547,58 @@ class ConsensusGroup:
         self.sendbuf = torch.zeros(max(topo.send_rows_total, 1), ROW, dtype=torch.float32, device=dev)
         self.recvbuf = torch.zeros(max(topo.recv_rows_total, 1), ROW, dtype=torch.float32, device=dev)
         self.scratch = self.ops.new_scratch(dev)
+        # Exchange transport between GPUs.  Default: the co-owners' receive buffers are mapped into this process
+        # (torch symmetric memory: CUDA peer memory over NVLink / NVSwitch) and the pack kernel writes every row
+        # straight into the buffer its consumer reads; two device-side barriers order a round.  Where that cannot
+        # be set up (one rank, CPU test double, no peer access) — or with p2p=False / DOGS_B200_ADMM_P2P=0 — the
+        # rows go through this rank's send buffer and batched NCCL send/recv.
+        self.p2p = None
+        self.p2p_error = None
+        want = (os.environ.get("DOGS_B200_ADMM_P2P", "1") != "0") if p2p is None else bool(p2p)
+        if want and self._world() > 1 and topo.exchange == "neighbour" and dev.type == "cuda" and isinstance(self.ops, CudaOps):
+            try:
+                self._setup_p2p(dev)
+            except Exception as ex:  # pylint: disable=W0703
+                self.p2p, self.p2p_error = None, repr(ex)
+        ok = torch.tensor([1 if self.p2p is not None else 0], dtype=torch.int32, device=dev)
+        if self._world() > 1 and dev.type == "cuda":
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)     # all ranks or none
+        if int(ok.item()) == 0:
+            self.p2p = None
         inv_n = [[1.0 / max(p.n_local * sz, 1) for sz in GROUP_SIZES] + [1.0] * 6 for p in (topo.plans[b] for b in sorted(topo.plans))]
         self._res_scale = torch.tensor(inv_n, dtype=torch.float64, device=dev)
 
     def _world(self):
         return dist.get_world_size(self.group) if _dist_on(self.group) else 1
+
+    def _setup_p2p(self, dev):
+        import torch.distributed._symmetric_memory as symm
+        topo = self.topo
+        group = self.group if self.group is not None else dist.group.WORLD
+        rows = torch.tensor([max(topo.recv_rows_total, 1)], dtype=torch.int64, device=dev)
+        dist.all_reduce(rows, op=dist.ReduceOp.MAX, group=self.group)          # symmetric: same size everywhere
+        buf = symm.empty(int(rows.item()), ROW, dtype=torch.float32, device=dev)
+        hdl = symm.rendezvous(buf, group)
+        tables = [None] * topo.world
+        dist.all_gather_object(tables, {f"{s_}:{r_}": v for (s_, r_), v in topo.msg_recv.items()}, group=self.group)
+        remote = sorted({r for p in topo.plans.values() for (_, r, _, _) in p.messages if r != topo.rank})
+        if len(remote) + 1 > 16:
+            raise RuntimeError("more than 15 peer GPUs co-own Gaussians with this rank")
+        slot_of_rank = {r: 1 + k for k, r in enumerate(remote)}
+        for a, p in topo.plans.items():
+            sel, row = [], []
+            for (b, r, first, n) in p.messages:
+                j = torch.arange(n, dtype=torch.int64)
+                if r == topo.rank:
+                    sel.append(torch.zeros(n, dtype=torch.uint8))
+                    row.append(first + j)                              # its place in this rank's own send buffer
+                else:
+                    sel.append(torch.full((n,), slot_of_rank[r], dtype=torch.uint8))
+                    row.append(int(tables[r][f"{a}:{b}"]) + j)          # its place in the receiver's buffer
+            p.p2p_sel = (torch.cat(sel) if sel else torch.zeros(0, dtype=torch.uint8)).to(dev)
+            p.p2p_row = (torch.cat(row) if row else torch.zeros(0, dtype=torch.int64)).to(torch.int32).to(dev)
+        self.recvbuf = buf
+        self.p2p = dict(hdl=hdl, dst_ptrs=[self.sendbuf.data_ptr()] + [int(hdl.buffer_ptrs[r]) for r in remote], remote=remote)
 
     @torch.no_grad()
     def consensus(self, adapt: bool = True):
@@ -550,6 +616,13 @@ class ConsensusGroup:
                 self.sendbuf.index_copy_(0, blk.plan.pack_dst.long(), tmp)
             if self._world() > 1 and topo.S_total > 0:
                 dist.all_reduce(self.sendbuf, op=dist.ReduceOp.SUM, group=self.group)
+        elif self.p2p is not None:
+            hdl = self.p2p["hdl"]
+            hdl.barrier(0)       # every co-owner has finished reading last round's rows
+            for b in order:
+                blk = self.blocks[b]
+                self.ops.pack_rows_to([t.detach() for t in blk.x], blk.plan, self.p2p["dst_ptrs"])
+            hdl.barrier(0)       # every row of this round is in place
         else:
             for b in order:
                 blk = self.blocks[b]

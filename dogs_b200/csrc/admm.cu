@@ -116,13 +116,21 @@ __device__ __forceinline__ RowLane row_lane(int lane) {
   return r;
 }
 
-struct PackArgs { const float* x[6]; };
+constexpr int ADMM_MAX_DESTS = 16;
+struct PackArgs {
+  const float* x[6];
+  float* dst[ADMM_MAX_DESTS];   // scatter mode: the buffers rows can go to (own send buffer, peers' receive buffers)
+};
 
 // out[r*59 + e] = x[src_local[r]][e] for the R rows this block sends to its co-owners (rows of all peers
 // concatenated; a Gaussian shared with three other blocks appears three times).  Replaces the six
 // per-tensor gathers + one torch.index_select per peer of the first version.
+// dst_sel != null: row r goes to a.dst[dst_sel[r]] at row dst_row[r] — the receive buffer of the co-owner's GPU,
+// mapped into this process (peer memory over NVLink): the pack kernel IS the exchange, there is no send buffer
+// to copy from and no collective call for these rows.
 __global__ void __launch_bounds__(ADMM_THREADS)
 admm_pack_rows_kernel(const __grid_constant__ PackArgs a, const int32_t* __restrict__ src_local,
+                      const uint8_t* __restrict__ dst_sel, const int32_t* __restrict__ dst_row,
                       int64_t R, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const RowLane rl = row_lane(lane);
@@ -134,8 +142,9 @@ admm_pack_rows_kernel(const __grid_constant__ PackArgs a, const int32_t* __restr
     const float v0 = __ldg(p0 + li * rl.sz[0] + rl.off[0]);
     float v1 = 0.f;
     if (p1) v1 = __ldg(p1 + li * rl.sz[1] + rl.off[1]);
-    out[r * ADMM_ROW + lane] = v0;
-    if (p1) out[r * ADMM_ROW + 32 + lane] = v1;
+    float* o = dst_sel ? a.dst[dst_sel[r]] + (int64_t)dst_row[r] * ADMM_ROW : out + r * ADMM_ROW;
+    o[lane] = v0;
+    if (p1) o[32 + lane] = v1;
   }
 }
 
@@ -296,8 +305,25 @@ extern "C" int admm_pack_rows(const AdmmConstTensors* x, const int32_t* src_loca
     a.x[g] = x->g[g];
     if (!a.x[g]) { set_error("admm_pack_rows: null tensor"); return 1; }
   }
-  admm_pack_rows_kernel<<<consensus_grid(R), ADMM_THREADS, 0, s>>>(a, src_local, R, out);
+  for (int k = 0; k < ADMM_MAX_DESTS; k++) a.dst[k] = nullptr;
+  admm_pack_rows_kernel<<<consensus_grid(R), ADMM_THREADS, 0, s>>>(a, src_local, nullptr, nullptr, R, out);
   return check_launch("admm_pack_rows", false, s);
+}
+
+extern "C" int admm_pack_rows_to(const AdmmConstTensors* x, const int32_t* src_local, const uint8_t* dst_sel,
+                                 const int32_t* dst_row, int64_t R, float* const* dsts, int32_t n_dsts, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (R <= 0) return 0;
+  if (!x || !src_local || !dst_sel || !dst_row || !dsts) { set_error("admm_pack_rows_to: null pointer"); return 1; }
+  if (n_dsts < 1 || n_dsts > ADMM_MAX_DESTS) { set_error("admm_pack_rows_to: 1..%d destination buffers", ADMM_MAX_DESTS); return 1; }
+  PackArgs a;
+  for (int g = 0; g < 6; g++) {
+    a.x[g] = x->g[g];
+    if (!a.x[g]) { set_error("admm_pack_rows_to: null tensor"); return 1; }
+  }
+  for (int k = 0; k < ADMM_MAX_DESTS; k++) a.dst[k] = k < n_dsts ? dsts[k] : nullptr;
+  admm_pack_rows_kernel<<<consensus_grid(R), ADMM_THREADS, 0, s>>>(a, src_local, dst_sel, dst_row, R, nullptr);
+  return check_launch("admm_pack_rows_to", false, s);
 }
 
 extern "C" int admm_consensus_update(const AdmmConstTensors* x, const AdmmTensors* u, const AdmmTensors* z,

@@ -287,6 +287,13 @@ typedef struct AdmmConstTensors { const float* g[ADMM_GROUPS]; } AdmmConstTensor
  * pack_rows: out[r*59 + :] = the 59 parameters of local Gaussian src_local[r], r < R (the rows for all
  * co-owners concatenated, each co-owner's rows ordered by global index). */
 int admm_pack_rows(const AdmmConstTensors* x, const int32_t* src_local, int64_t R, float* out, void* stream);
+/* The same gather with a destination per row: row r goes to dsts[dst_sel[r]] (<= 16 buffers of [rows, 59] floats)
+ * at row dst_row[r].  With the co-owners' receive buffers mapped into this process (peer memory over NVLink /
+ * NVSwitch, e.g. torch symmetric memory) the pack kernel writes every row straight where its consumer reads it:
+ * pack and exchange are one kernel, and no NCCL call is made for the rows. */
+int admm_pack_rows_to(const AdmmConstTensors* x, const int32_t* src_local, const uint8_t* dst_sel,
+                      const int32_t* dst_row, int64_t R, float* const* dsts /* host array of device pointers */,
+                      int32_t n_dsts, void* stream);
 /* consensus_update over ALL n Gaussians of the block.
  *   shared_row[i] < 0: owned by this block only: z = x, u untouched (the reference's average with count 1).
  *   shared_row[i] = s: z = (sum of the addends of row s) / count[s]; u += relax * (x - z).
