@@ -392,6 +392,7 @@ def main():
     ap.add_argument("--unfused-loss", action="store_true",
                     help="ours: evaluate the loss with torch ops around fused_ssim, as the reference's trainer does")
     ap.add_argument("--no-clocks", action="store_true", help="do not query NVML inside the timed region")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the separately timed blend_bwd launches (ncu launch lists)")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3)
 
@@ -584,7 +585,7 @@ def main():
 
     # ---- roofline of the dominant kernel (blend backward), timed live with CUDA events ---------------------------
     roofline, stats = None, {}
-    if ours and rank == 0:
+    if ours and rank == 0 and not args.no_roofline:
         roofline, stats = blend_bwd_roofline(sc, dev)
 
     # ---- extras at N = 1: the other single-GPU configs, and the N > 1 step on one GPU --------------------------

@@ -24,7 +24,7 @@ namespace dogs {
 // `gaussian_count[id]++` is a non-atomic race; here the lanes of a warp are tallied with a ballot,
 // tiles add up in shared memory and one integer atomic per (tile, Gaussian) reaches global memory).
 template <bool COUNT>
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(TILE_PIX, 8)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                  const uint32_t* __restrict__ point_list, int W,
                  int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
