@@ -133,7 +133,7 @@ def load_modules(impl):
 
 
 # ---- CPU baselines (reported, not optimised; rank 0, N = 1) ----------------------------------------------------
-def cpu_baseline_port(scene_cpu, n_tiles_sample=48, seed=0):
+def cpu_baseline_port(scene_cpu, n_tiles_sample=160, seed=0):
     """The scalar C oracle (kind 'port', 1 thread) on a bounded sample: preprocess + binning of ALL Gaussians,
     blend forward + backward on a random subset of tiles scaled to the full image."""
     import numpy as np

@@ -380,6 +380,11 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         V3 dLc = {g_color[0], g_color[1], g_color[2]};
         V3 dm = sh_backward(D, M, pos, cp, clamped[idx], dLc, sh_row, g_dc);
         g_mean3D.x += dm.x; g_mean3D.y += dm.y; g_mean3D.z += dm.z;
+      } else if (dL_ddc != nullptr) {
+        // degree-0 model without a rest tensor (M == 0): the colour is SH_C0 * dc + 0.5 and only dc gets a gradient
+        // (the reference's `if (shs)` branch, backward.cu:445-447, is never taken for it and its dc never trains)
+        const uint32_t cl = clamped[idx];
+        g_dc = {(cl & 1u) ? 0.f : SH_C0 * g_color[0], (cl & 2u) ? 0.f : SH_C0 * g_color[1], (cl & 4u) ? 0.f : SH_C0 * g_color[2]};
       }
 
       g_opacity = dL_dopac;

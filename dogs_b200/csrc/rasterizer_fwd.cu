@@ -398,6 +398,9 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
     big &= big - 1;
     const uint32_t idx = __shfl_sync(full, e.y, src);
     uint32_t o = __shfl_sync(full, off, src);
+    // the count was taken by preprocess with the same test; should the two ever disagree (different FMA placement
+    // at the two inlining sites), stay inside this Gaussian's own slots
+    const uint32_t o_end = o + __shfl_sync(full, cnt, src);
     const float4 b = rec[idx].b;
     const float2 xy = {b.x, b.y};
     uint2 rect_min, rect_max;
@@ -419,7 +422,7 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
       const unsigned bal = __ballot_sync(full, r);
       if (r) {
         const uint32_t pos = o + __popc(bal & ((1u << lane) - 1u));
-        if (pos < capacity) {
+        if (pos < capacity && pos < o_end) {
           tile_keys[pos] = y * gx + x;
           vals[pos] = idx;
         }
@@ -433,7 +436,7 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
 // Four consecutive keys per thread (one 16-byte load + the predecessor).
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(uint32_t L_cap, const uint32_t* __restrict__ L_dev, const uint32_t* __restrict__ tile_keys,
-                   uint2* __restrict__ ranges) {
+                   uint2* __restrict__ ranges, uint32_t T) {
   pdl_wait();
   pdl_trigger();
   const uint32_t L = L_dev ? min(*L_dev, L_cap) : L_cap;
@@ -452,13 +455,15 @@ tile_ranges_kernel(uint32_t L_cap, const uint32_t* __restrict__ L_dev, const uin
   for (uint32_t q = 0; q < 4; q++) {
     if (q >= n) break;
     const uint32_t idx = i0 + q, cur = k[q];
-    if (idx == 0) {
-      ranges[cur].x = 0;
-    } else if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
+    if (cur < T) {        // (a slot the emit stage left unwritten would carry garbage: never index with it)
+      if (idx == 0) {
+        ranges[cur].x = 0;
+      } else if (cur != prev) {
+        if (prev < T) ranges[prev].y = idx;
+        ranges[cur].x = idx;
+      }
+      if (idx == L - 1) ranges[cur].y = L;
     }
-    if (idx == L - 1) ranges[cur].y = L;
     prev = cur;
   }
 }
@@ -628,7 +633,7 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* R_dev, 
                        uint2* ranges, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
-  if (R > 0) launch_pdl(tile_ranges_kernel, dim3((R + 1023) / 1024), dim3(256), 0, s, R, R_dev, tile_keys, ranges);
+  if (R > 0) launch_pdl(tile_ranges_kernel, dim3((R + 1023) / 1024), dim3(256), 0, s, R, R_dev, tile_keys, ranges, gx * gy);
   return check_launch("tile_ranges", prm.debug != 0, s);
 }
 

@@ -109,7 +109,7 @@ def _ssim(a, b):
     return (((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2))).mean()
 
 
-def measure(scene_cpu, n_tiles=48, seed=0, unit="iters/s"):
+def measure(scene_cpu, n_tiles=384, seed=0, unit="iters/s"):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sc = scene_cpu

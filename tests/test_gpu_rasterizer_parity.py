@@ -269,6 +269,17 @@ def test_edge_cases():
     b = rast(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"], shs=sc["sh"], dc=sc["dc"],
              scales=sc["scales"], rotations=sc["rotations"])[0]
     assert torch.equal(a, b)
+    # (f) a degree-0 model WITHOUT a rest tensor (M == 0) trains its dc colours: same gradient as with an unused rest tensor
+    grads = []
+    sc0 = dict(sc, sh_degree=0)
+    for shs in (sc["sh"], sc["sh"][:, :0].contiguous()):
+        dcp = sc["dc"].clone().requires_grad_(True)
+        r0 = mine.GaussianRasterizer(scenes.raster_settings(mine, sc0))
+        img0 = r0(means3D=sc["means3D"], means2D=torch.zeros_like(sc["means3D"]), opacities=sc["opacities"], shs=shs, dc=dcp,
+                  scales=sc["scales"], rotations=sc["rotations"])[0]
+        img0.square().sum().backward()
+        grads.append(dcp.grad.clone())
+    assert float(grads[0].abs().max()) > 0 and U.rel_to_max(grads[1], grads[0]) <= 1e-6     # (float reductions in run order)
     # (e) CPU tensors are rejected loudly: there is no CPU fallback
     with pytest.raises(RuntimeError, match="no CPU path"):
         rast(means3D=sc["means3D"].cpu(), means2D=sc["means3D"].cpu(), opacities=sc["opacities"].cpu(),
