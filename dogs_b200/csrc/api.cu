@@ -88,16 +88,17 @@ GeomState GeomState::carve(char* p, size_t P) {
   g.ctl = c.take<uint32_t>(16);
   return g;
 }
-size_t BinState::bytes(size_t R) {
+size_t BinState::bytes(size_t R, size_t T) {
   Carver c(nullptr);
-  c.take<uint32_t>(R); c.take<uint32_t>(R);
+  c.take<uint32_t>(R); c.take<uint32_t>(R); c.take<uint32_t>(8 * hit_slots(R, T));
   return c.off;
 }
-BinState BinState::carve(char* p, size_t R) {
+BinState BinState::carve(char* p, size_t R, size_t T) {
   Carver c(p);
   BinState b;
   b.point_list = c.take<uint32_t>(R);
   b.tile_keys = c.take<uint32_t>(R);
+  b.hits = c.take<uint32_t>(8 * hit_slots(R, T));
   return b;
 }
 size_t ImgState::bytes(size_t N, size_t T) {
@@ -171,7 +172,7 @@ int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t R, DgrLayout* out) {
   const size_t N = (size_t)W * H;
   const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
   GeomState g = GeomState::carve(nullptr, P);
-  BinState b = BinState::carve(nullptr, R);
+  BinState b = BinState::carve(nullptr, R, T);
   ImgState im = ImgState::carve(nullptr, N, T);
   out->geom_record = (size_t)g.rec;
   out->geom_clamped = (size_t)g.clamped;
@@ -179,7 +180,7 @@ int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t R, DgrLayout* out) {
   out->geom_bytes = GeomState::bytes(P);
   out->bin_point_list = (size_t)b.point_list;
   out->bin_tile_keys = (size_t)b.tile_keys;
-  out->bin_bytes = BinState::bytes(R);
+  out->bin_bytes = BinState::bytes(R, T);
   out->img_ranges = (size_t)im.ranges;
   out->img_final_T = (size_t)im.final_T;
   out->img_n_contrib = (size_t)im.n_contrib;
@@ -241,15 +242,15 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
   if (!rb) { set_error("forward: cannot create the pinned read-back slot"); return 1; }
   const int bits = higher_msb((uint32_t)T);
   const int passes = (bits + 7) / 8;
-  BinState b = BinState::carve(nullptr, 0);
+  BinState b = BinState::carve(nullptr, 0, T);
   size_t bin_bytes = 0;
 
   // stages after the scan, for a binning buffer of `cap` rows; dev_count: take R from g.ctl[2]
   auto bin_and_blend = [&](uint32_t cap, bool dev_count) -> int {
-    bin_bytes = BinState::bytes(cap);
+    bin_bytes = BinState::bytes(cap, T);
     char* bin_p = binning_alloc(binning_user, bin_bytes > 0 ? bin_bytes : 256);
     if (!bin_p) { set_error("binning allocation failed"); return 1; }
-    b = BinState::carve(bin_p, cap);
+    b = BinState::carve(bin_p, cap, T);
     rows = cap;
     const uint32_t* R_dev = dev_count ? g.ctl + 2 : nullptr;
     if (cap > 0) {
@@ -368,7 +369,7 @@ int dgr_backward(const DgrParams* prm, int32_t num_rendered, const float* means3
   const size_t P = p.P, N = (size_t)p.W * p.H;
   const size_t T = (size_t)((p.W + TILE_X - 1) / TILE_X) * ((p.H + TILE_Y - 1) / TILE_Y);
   GeomState g = GeomState::carve(const_cast<char*>(geom), P);
-  BinState b = BinState::carve(const_cast<char*>(binning), (size_t)num_rendered);
+  BinState b = BinState::carve(const_cast<char*>(binning), (size_t)num_rendered, T);
   ImgState im = ImgState::carve(const_cast<char*>(image), N, T);
   const bool pen_sums = p.admm && p.admm->zmu_xyz && p.admm->sums;
   float* accum = reinterpret_cast<float*>(

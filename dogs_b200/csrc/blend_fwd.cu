@@ -16,6 +16,10 @@
 //     final_T / n_contrib (blend_bwd.cu).
 #include "blend_common.cuh"
 
+#ifndef BF_MIN_CTAS
+#define BF_MIN_CTAS 8
+#endif
+
 namespace dogs {
 
 // COUNT = true additionally counts, per Gaussian, the pixels it was blended into (LightGaussian
@@ -24,19 +28,20 @@ namespace dogs {
 // `gaussian_count[id]++` is a non-atomic race; here the lanes of a warp are tallied with a ballot,
 // tiles add up in shared memory and one integer atomic per (tile, Gaussian) reaches global memory).
 template <bool COUNT>
-__global__ void __launch_bounds__(TILE_PIX, 8)
+__global__ void __launch_bounds__(TILE_PIX, BF_MIN_CTAS)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
                  const uint32_t* __restrict__ point_list, int W,
                  int H, const SplatRecord* __restrict__ rec, const float* __restrict__ bg_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                  float* __restrict__ out_color, float* __restrict__ invdepth,
                  float* __restrict__ pix_color, float* __restrict__ pix_invdepth,
-                 int* __restrict__ gaussian_count) {
+                 int* __restrict__ gaussian_count, uint32_t* __restrict__ hits) {
   __shared__ float4 sA[2][TILE_PIX];
   __shared__ float4 sB[2][TILE_PIX];
   __shared__ float4 sC[2][TILE_PIX];
   __shared__ uint32_t sId[COUNT ? 2 : 1][COUNT ? TILE_PIX : 1];
   __shared__ int sCnt[COUNT ? TILE_PIX : 1];
+  __shared__ uint32_t sHit[2][TILE_PIX / 32][8];   // [buffer][group of 32 entries][8x4 block = warp]
   if (COUNT) sCnt[threadIdx.x] = 0;
   pdl_wait();
   pdl_trigger();
@@ -78,10 +83,21 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   };
   if (rounds > 0) fetch(0, 0);
 
-  for (int i = 0; i < rounds; i++, toDo -= TILE_PIX) {
+  // The reachability words of a batch go out to the backward pass (BinState::hits) one barrier later, as one
+  // contiguous store of up to 256 bytes by the first 64 threads.  (Nothing is carried across the blend loop for
+  // it: the kernel runs on 32 registers.)
+  auto flush_hits = [&](int round, int left) {       // left = list entries from the start of `round` on
+    const int groups = (min(TILE_PIX, left) + 31) / 32;
+    if ((int)tid < groups * 8)
+      hits[((size_t)(range.x / 32) + tile + (size_t)round * (TILE_PIX / 32)) * 8 + tid] = sHit[round & 1][tid >> 3][tid & 7];
+  };
+
+  int i = 0;
+  for (; i < rounds; i++, toDo -= TILE_PIX) {
     const int buf = i & 1;
     // forward.cu:415-417 (the barrier also frees buffer buf^1, last read in round i-1)
     int num_done = __syncthreads_count(done);
+    if (i > 0) flush_hits(i - 1, toDo + TILE_PIX);
     if (num_done == TILE_PIX) break;
     if (i + 1 < rounds) fetch(i + 1, buf ^ 1); else cp_async_commit();
     cp_async_wait<1>();
@@ -100,6 +116,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         h = block_reachable(sA[buf][j], b.x, b.y, rx0, ry0, rx1, ry1, sC[buf][j].w);
       }
       hit[r] = __ballot_sync(0xffffffffu, h);
+      if (lane == r) sHit[buf][r][warp] = hit[r];
     }
 
 #pragma unroll
@@ -148,6 +165,10 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
   }
   cp_async_wait<0>();
+  if (i == rounds && rounds > 0) {      // the loop ran to its end: the last batch is still in shared memory
+    __syncthreads();
+    flush_hits(rounds - 1, toDo + TILE_PIX);
+  }
 
   if (inside) {
     final_T[pix_id] = T;
@@ -181,14 +202,14 @@ int launch_blend_fwd(const DgrParams& prm, const GeomState& g, const BinState& b
     cudaMemsetAsync(prm.gaussians_count, 0, (size_t)prm.P * sizeof(int32_t), s);
     blend_fwd_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, im.tile_order, b.point_list, prm.W, prm.H, g.rec, prm.bg,
                                                      im.final_T, im.n_contrib, out_color, out_invdepth,
-                                                     im.pix_color, im.pix_invdepth, prm.gaussians_count);
+                                                     im.pix_color, im.pix_invdepth, prm.gaussians_count, b.hits);
     if (prm.important_score)
       importance_kernel<<<(prm.P + 255) / 256, 256, 0, s>>>(prm.P, prm.gaussians_count, g.rec, prm.important_score);
     return check_launch("blend_fwd(count)", prm.debug != 0, s, prm.important_score ? 2 : 1);
   }
   launch_pdl(blend_fwd_kernel<false>, dim3(grid), dim3(TILE_PIX), 0, s, (const uint2*)im.ranges, (const uint32_t*)im.tile_order,
              (const uint32_t*)b.point_list, (int)prm.W, (int)prm.H, (const SplatRecord*)g.rec, prm.bg, im.final_T, im.n_contrib,
-             out_color, out_invdepth, im.pix_color, im.pix_invdepth, (int*)nullptr);
+             out_color, out_invdepth, im.pix_color, im.pix_invdepth, (int*)nullptr, b.hits);
   return check_launch("blend_fwd", prm.debug != 0, s);
 }
 

@@ -267,8 +267,14 @@ struct GeomState {
 };
 struct BinState {
   uint32_t* point_list; uint32_t* tile_keys;
-  static size_t bytes(size_t R);
-  static BinState carve(char* p, size_t R);
+  // Sub-tile reachability found by the forward blend, reused by the backward: for every group of 32 consecutive
+  // list entries of a tile, one word per 8x4 pixel block of the tile (8 words = 32 bytes per group; bit = entry
+  // can reach the block, blend_common.cuh).  Group q of tile t sits in slot range.x/32 + t + q — the "+ t" keeps
+  // the slots of neighbouring tiles apart although their lists do not start on multiples of 32.
+  uint32_t* hits;
+  static size_t hit_slots(size_t R, size_t T) { return R / 32 + T + 16; }
+  static size_t bytes(size_t R, size_t T);
+  static BinState carve(char* p, size_t R, size_t T);
 };
 struct ImgState {
   uint2* ranges; uint32_t* tile_order;   // tile ids, longest list first: the launch order of the blend kernels

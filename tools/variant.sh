@@ -10,5 +10,5 @@ obj=dogs_b200/build/variants/${src%.cu}_$name.o
   -c dogs_b200/csrc/$src -o $obj 2> dogs_b200/build/variants/${src%.cu}_$name.ptxas.log
 objs=$(ls dogs_b200/build/*.o | grep -v "/${src%.cu}\.o$")
 /usr/local/cuda/bin/nvcc -shared -o dogs_b200/build/lib_$name.so $objs $obj -lcudart
-grep -A1 "radix_pass\|$3" dogs_b200/build/variants/${src%.cu}_$name.ptxas.log | grep "Used" | head -3
+grep "Used\|spill" dogs_b200/build/variants/${src%.cu}_$name.ptxas.log | head -6
 echo dogs_b200/build/lib_$name.so
