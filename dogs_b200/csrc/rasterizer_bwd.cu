@@ -278,9 +278,15 @@ __device__ __forceinline__ void cov_chain_bwd(const float3 mean_f, const float3 
 #ifndef DOGS_PREB_REAL
 #define DOGS_PREB_REAL double
 #endif
-constexpr int PREB_THREADS = 128;
+#ifndef PREB_THREADS_N
+#define PREB_THREADS_N 128
+#endif
+#ifndef PREB_MIN_CTAS
+#define PREB_MIN_CTAS 5
+#endif
+constexpr int PREB_THREADS = PREB_THREADS_N;
 
-__global__ void __launch_bounds__(PREB_THREADS, 5)
+__global__ void __launch_bounds__(PREB_THREADS, PREB_MIN_CTAS)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       const int* __restrict__ radii, const float* __restrict__ dc,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
