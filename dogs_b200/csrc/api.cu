@@ -254,13 +254,13 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     rows = cap;
     const uint32_t* R_dev = dev_count ? g.ctl + 2 : nullptr;
     if (cap > 0) {
-      scratch2_bytes = align_up((size_t)cap * 4) * 2 + sort_pairs_scratch_bytes(cap) + 256;
+      scratch2_bytes = align_up((size_t)cap * 4) * 2 + sort_pairs_scratch_bytes(cap, passes) + 256;
       char* sc = scratch_alloc(scratch_user, scratch2_bytes);
       if (!sc) { set_error("scratch allocation failed"); return 1; }
       Carver cv(sc);
       uint32_t* keys_u = cv.take<uint32_t>(cap);
       uint32_t* vals_u = cv.take<uint32_t>(cap);
-      char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(cap));
+      char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(cap, passes));
       // arrange the ping-pong so that the last pass lands in the persistent binning buffers
       uint32_t *ka, *va, *kb, *vb;
       if (passes % 2 == 0) { ka = b.tile_keys; va = b.point_list; kb = keys_u; vb = vals_u; }
@@ -287,14 +287,14 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
                               cov3D_precomp, radii, g, s)) return 1;
     clk.mark();   // [0] preprocess
     // depth order of the Gaussians (ties broken by index: the sort is stable)
-    scratch1_bytes = align_up(P * 4) * 2 + sort_pairs_scratch_bytes(P) + scan_scratch_bytes(P) + 256;
+    scratch1_bytes = align_up(P * 4) * 2 + sort_pairs_scratch_bytes(P) + gather_scan_scratch_bytes(P) + 256;
     char* sc = scratch_alloc(scratch_user, scratch1_bytes);
     if (!sc) { set_error("scratch allocation failed"); return 1; }
     Carver cv(sc);
     uint32_t* keys_b = cv.take<uint32_t>(P);
     uint32_t* vals_b = cv.take<uint32_t>(P);
     char* sort_scratch = cv.take<char>(sort_pairs_scratch_bytes(P));
-    char* scan_scratch = cv.take<char>(scan_scratch_bytes(P));
+    char* scan_scratch = cv.take<char>(gather_scan_scratch_bytes(P));
     // Depth order.  Positive floats of one scene share their top bits, so only the low `key_bits` bits — up to
     // the highest bit in which the smallest and the largest key differ — need sorting (3 passes of 8 bits instead
     // of 4 for depths within a factor of ~2-4).  The host cannot know that range yet, so it sorts on the bits the
@@ -305,10 +305,9 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
       int in_b = 0;
       if (sort_pairs_u32(g.depth_key, g.sorted_idx, keys_b, vals_b, P, 0, key_bits, sort_scratch, dbg, s, &in_b, true)) return 1;
       clk.mark();   // [1] depth sort
-      // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order;
-      // the scan and the emit kernel then stream sequentially
-      if (launch_gather_emit(p, g, in_b ? vals_b : g.sorted_idx, s)) return 1;
-      return exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, g.ctl + 2, P, scan_scratch, dbg, s);
+      // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order, and the same
+      // kernel scans the instance counts (offsets, R): the emit kernel then streams sequentially
+      return launch_gather_scan(p, g, in_b ? vals_b : g.sorted_idx, scan_scratch, g.ctl + 2, s);
     };
     const int bits_assumed = (p.depth_key_bits >= 1 && p.depth_key_bits <= 32) ? p.depth_key_bits : 32;
     if (depth_stage(bits_assumed)) return 1;

@@ -297,7 +297,8 @@ static inline int significant_key_bits(uint32_t kmin, uint32_t kmax) {
   while (d) { hb++; d >>= 1; }
   return hb;
 }
-size_t sort_pairs_scratch_bytes(size_t n);
+// max_passes: digit passes (8 bits each) the caller will ask for at most, 1..4
+size_t sort_pairs_scratch_bytes(size_t n, int max_passes = 4);
 // Stable LSD sort of (key,val) u32 pairs on bits [begin_bit,end_bit), 8 bits per pass, ping-pong
 // between the (a) and (b) buffers starting from (a); *result_in_b tells where the result is.
 int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
@@ -316,7 +317,9 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
                           const float* scales, const float* rotations, const float* cov3D_precomp,
                           int32_t* radii, GeomState& g, cudaStream_t s);
 int launch_depth_keys(const DgrParams& prm, const GeomState& g, cudaStream_t s);
-int launch_gather_emit(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, cudaStream_t s);
+size_t gather_scan_scratch_bytes(size_t P);
+int launch_gather_scan(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, char* scratch,
+                       uint32_t* total_out, cudaStream_t s);
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
                 uint32_t* vals, uint32_t capacity, cudaStream_t s);
 // R_cap: rows the launch is sized for; R_dev (nullable): actual count in device memory

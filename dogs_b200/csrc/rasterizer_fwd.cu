@@ -322,6 +322,94 @@ gather_emit_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* 
   sorted_emit[j] = make_uint4(e.x, id, e.z, e.w);
 }
 
+// Small models: the gather and the exclusive scan of the instance counts in depth order (duplicateWithKeys'
+// offsets, rasterizer_impl.cu:447-452 + cub::DeviceScan::InclusiveSum) in ONE kernel instead of four.  The scan is
+// chained: a CTA takes its chunk number from a ticket counter, publishes the chunk total, and warp 0 looks back
+// over the status words of the chunks before it, 32 at a time (2 flag bits + 30-bit value: total first, inclusive
+// prefix once known).  A chunk a CTA waits for is owned by a CTA that already runs, so the wait cannot deadlock.
+// (Measured: 0.026 vs 0.025 ms at C1 with three launches less; at 3 M Gaussians the chain of prefixes sets the
+// pace — 0.069 ms against 0.055 ms for gather + three-kernel scan, and wider look-back windows, back-off and larger
+// chunks all made it slower — so large models keep the separate kernels.)
+constexpr int GS_THREADS = 256, GS_ITEMS = 4, GS_CHUNK = GS_THREADS * GS_ITEMS;
+constexpr uint32_t GS_LOCAL = 1u << 30, GS_INCL = 2u << 30, GS_VALUE = (1u << 30) - 1u;
+constexpr size_t GS_CHAINED_MAX = 1u << 18;     // Gaussians up to which the chained kernel is used
+__global__ void __launch_bounds__(GS_THREADS)
+gather_scan_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* __restrict__ emit_rec,
+                   uint4* __restrict__ sorted_emit, uint32_t* __restrict__ sorted_cnt, uint32_t* __restrict__ offsets,
+                   uint32_t* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t* __restrict__ total_out) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ uint32_t wsum[GS_THREADS / 32];
+  __shared__ uint32_t s_chunk, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t chunk = s_chunk;
+  const int j0 = (int)chunk * GS_CHUNK + tid * GS_ITEMS;
+  uint32_t id[GS_ITEMS];
+  uint4 e[GS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < GS_ITEMS; k++) id[k] = j0 + k < P ? sorted_idx[j0 + k] : 0u;
+#pragma unroll
+  for (int k = 0; k < GS_ITEMS; k++) e[k] = j0 + k < P ? emit_rec[id[k]] : make_uint4(0u, 0u, 0u, 0u);
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < GS_ITEMS; k++) sum += e[k].y;
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  uint32_t woff = 0;
+#pragma unroll
+  for (int w = 0; w < GS_THREADS / 32; w++) if (w < warp) woff += wsum[w];
+  if (warp == 0) {
+    uint32_t total = lane < GS_THREADS / 32 ? wsum[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    uint32_t before = 0;
+    if (chunk > 0) {
+      if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(status + chunk), "r"(GS_LOCAL | total) : "memory");
+      int t = (int)chunk - 1;                    // lane l looks at chunk t - l
+      while (true) {
+        uint32_t sv = GS_INCL;                    // before chunk 0: an inclusive prefix of 0
+        if (t - lane >= 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv) : "l"(status + (t - lane)) : "memory");
+        const uint32_t f = sv >> 30;
+        const uint32_t incl = __ballot_sync(0xffffffffu, f == 2), ready = __ballot_sync(0xffffffffu, f != 0);
+        // lanes 0..last are needed: up to the nearest inclusive prefix, or all 32
+        const int last = incl ? __ffs(incl) - 1 : 31;
+        const uint32_t need = last == 31 ? 0xffffffffu : (2u << last) - 1u;
+        if ((ready & need) != need) continue;     // something in that span is not published yet: poll again
+        uint32_t v = lane <= last ? (sv & GS_VALUE) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        before += v;
+        if (incl) break;
+        t -= 32;
+      }
+    }
+    if (lane == 0) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(status + chunk), "r"(GS_INCL | (before + total)) : "memory");
+      s_base = before;
+      if ((int)(chunk + 1) * GS_CHUNK >= P) *total_out = before + total;   // the last chunk: R
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_base + woff + x - sum;
+#pragma unroll
+  for (int k = 0; k < GS_ITEMS; k++) {
+    if (j0 + k < P) {
+      sorted_cnt[j0 + k] = e[k].y;
+      offsets[j0 + k] = off;
+      sorted_emit[j0 + k] = make_uint4(e[k].x, id[k], e[k].z, e[k].w);
+    }
+    off += e[k].y;
+  }
+}
+
 // Position of the (k+1)-th set bit of a 64-bit mask (k < popcount).
 __device__ __forceinline__ int kth_set_bit64(uint32_t lo, uint32_t hi, int k) {
   const int nlo = __popc(lo);
@@ -614,10 +702,28 @@ int launch_depth_keys(const DgrParams& prm, const GeomState& g, cudaStream_t s) 
   return check_launch("depth_keys", prm.debug != 0, s);
 }
 
-int launch_gather_emit(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, cudaStream_t s) {
-  launch_pdl(gather_emit_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, sorted_idx,
-             (const uint4*)g.emit_rec, g.sorted_emit, g.sorted_cnt);
-  return check_launch("gather_emit", prm.debug != 0, s);
+size_t gather_scan_scratch_bytes(size_t P) {
+  if (P <= GS_CHAINED_MAX) return align_up(((P + GS_CHUNK - 1) / GS_CHUNK + 2) * sizeof(uint32_t));
+  return scan_scratch_bytes(P);
+}
+
+// sorted_emit / sorted_cnt / offsets in depth order and the instance total R (to *total_out)
+int launch_gather_scan(const DgrParams& prm, const GeomState& g, const uint32_t* sorted_idx, char* scratch,
+                       uint32_t* total_out, cudaStream_t s) {
+  if ((size_t)prm.P > GS_CHAINED_MAX) {
+    // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order; the scan and
+    // the emit kernel then stream sequentially
+    launch_pdl(gather_emit_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, sorted_idx,
+               (const uint4*)g.emit_rec, g.sorted_emit, g.sorted_cnt);
+    if (int e = check_launch("gather_emit", prm.debug != 0, s)) return e;
+    return exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, total_out, prm.P, scratch, prm.debug != 0, s);
+  }
+  const uint32_t nchunks = (prm.P + GS_CHUNK - 1) / GS_CHUNK;
+  uint32_t* status = reinterpret_cast<uint32_t*>(scratch);
+  cudaMemsetAsync(scratch, 0, gather_scan_scratch_bytes(prm.P), s);
+  launch_pdl(gather_scan_kernel, dim3(nchunks), dim3(GS_THREADS), 0, s, (int)prm.P, sorted_idx, (const uint4*)g.emit_rec,
+             g.sorted_emit, g.sorted_cnt, g.offsets, status, status + nchunks, total_out);
+  return check_launch("gather_scan", prm.debug != 0, s);
 }
 
 int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, uint32_t* tile_keys,
