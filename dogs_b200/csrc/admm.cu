@@ -167,98 +167,211 @@ struct ConsensusArgs {
 //   zmu = z - u for the per-iteration penalty.  Residual sums in FP64: partial[blk][g] = sum (z - x)^2
 //   (primal, master:396-432), partial[blk][6+g] = sum (z_prev - z)^2 / count (dual, master:435-456: every
 //   global Gaussian once); the last CTA to finish folds the partials in a fixed order into residuals[12].
-// MAXA > 0: at most MAXA addends per row, all table entries and all addend rows are fetched before anything is
-// summed (independent loads in flight instead of an entry -> row -> entry -> row chain); MAXA = 0: any number.
+//
+// Work layout (second version).  The first one gave a warp one Gaussian: its 59 floats sit in six tensors, so
+// every load or store instruction of the warp touched up to six different cache lines and used 12-180 bytes of
+// each — the kernel ran at 35 % of the HBM peak, bound by the L1 tag stage, not by DRAM.  Now a CTA takes a tile
+// of 256 consecutive Gaussians, stages their table entries (shared row, owner count, addend entries) in shared
+// memory once, and then walks the tile TENSOR BY TENSOR: the tile's slice of a tensor is one contiguous run
+// (256 x 3 ... 256 x 45 floats), consecutive threads take consecutive floats, four floats per thread are in
+// flight before anything is summed.  Addend rows come from the 59-float exchange rows; the floats of one group
+// are contiguous there as well.
+constexpr int CT_ROWS = 256;          // Gaussians per tile
+#ifndef CT_MIN_CTAS
+#define CT_MIN_CTAS 4
+#endif
+constexpr uint32_t ENT_NONE = 0xffffffffu;
+
+template <int SZ>
+__device__ __noinline__ void consensus_group_tail(const ConsensusArgs& a, int g, int row_off, int64_t i0, int rows,
+                                                  const int32_t* s_sr, const uint8_t* s_cnt, const uint32_t* s_ent,
+                                                  int max_addends, float relax, bool has_zmu, const double* inv_cnt,
+                                                  double* s_acc);
+// One element: average / dual update / residual terms (shared by the vector and the tail path).
+__device__ __forceinline__ void consensus_element(const ConsensusArgs& a, int row_off, int c, int32_t sr, int cnt_i,
+                                                  const uint32_t* ent, int max_addends, float relax, float xv, float zo,
+                                                  float uv, const double* inv_cnt, float& z_new, float& u_new,
+                                                  double& primal, double& dual) {
+  z_new = xv;
+  u_new = uv;
+  if (sr >= 0) {
+    float sum = 0.f;
+    for (int j = 0; j < max_addends; j++) {
+      const uint32_t en = ent[j];
+      if (en == ENT_NONE) break;
+      const uint32_t which = en >> 28;
+      const float v = which == 15u ? xv : __ldg(a.src[which] + (int64_t)(en & 0x0fffffffu) * ADMM_ROW + row_off + c);
+      sum = j == 0 ? v : __fadd_rn(sum, v);
+    }
+    z_new = __fdiv_rn(sum, (float)cnt_i);
+    u_new = __fadd_rn(uv, __fmul_rn(relax, __fsub_rn(xv, z_new)));
+  }
+  const double dp = (double)z_new - (double)xv, dd = (double)zo - (double)z_new;
+  primal += dp * dp;
+  dual += dd * dd * inv_cnt[cnt_i];
+}
+
+template <int SZ>
+__device__ __noinline__ void consensus_group_tail(const ConsensusArgs& a, int g, int row_off, int64_t i0, int rows,
+                                                  const int32_t* s_sr, const uint8_t* s_cnt, const uint32_t* s_ent,
+                                                  int max_addends, float relax, bool has_zmu, const double* inv_cnt,
+                                                  double* s_acc) {
+  double primal = 0.0, dual = 0.0;
+  const float* xg = a.x[g] + i0 * SZ;
+  float* ug = a.u[g] + i0 * SZ;
+  float* zg = a.z[g] + i0 * SZ;
+  float* mg = has_zmu ? a.zmu[g] + i0 * SZ : nullptr;
+  for (int e = threadIdx.x; e < rows * SZ; e += ADMM_THREADS) {
+    const int r = e / SZ, c = e - r * SZ;
+    const int32_t sr = s_sr[r];
+    float z_new, u_new;
+    consensus_element(a, row_off, c, sr, sr >= 0 ? (int)s_cnt[r] : 1, s_ent + r * max_addends, max_addends, relax, xg[e],
+                      zg[e], ug[e], inv_cnt, z_new, u_new, primal, dual);
+    zg[e] = z_new;
+    if (sr >= 0) ug[e] = u_new;
+    if (has_zmu) mg[e] = z_new - u_new;
+  }
+  s_acc[g * ADMM_THREADS + threadIdx.x] += primal;
+  s_acc[(6 + g) * ADMM_THREADS + threadIdx.x] += dual;
+}
+
+// A full tile of one tensor as 16-byte vectors: 256 x SZ floats, contiguous and 16-byte aligned.
+// MAXA > 0: at most MAXA addends per Gaussian; the (up to) 4 x MAXA addend floats of a vector are all requested
+// before anything is summed — taken one after the other (load, add, next entry, load ...) the gathers formed a
+// chain of up to 12 memory round trips per vector.  MAXA = 0: any number of addends, sequential.
+template <int SZ, int MAXA>
+__device__ __forceinline__ void consensus_group(const ConsensusArgs& a, int g, int row_off, int64_t i0,
+                                                const int32_t* s_sr, const uint8_t* s_cnt, const uint32_t* s_ent,
+                                                int max_addends, float relax, bool has_zmu, const double* inv_cnt,
+                                                double* s_acc) {
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.x[g] + i0 * SZ);
+  float4* __restrict__ u4 = reinterpret_cast<float4*>(a.u[g] + i0 * SZ);
+  float4* __restrict__ z4 = reinterpret_cast<float4*>(a.z[g] + i0 * SZ);
+  float4* __restrict__ m4 = has_zmu ? reinterpret_cast<float4*>(a.zmu[g] + i0 * SZ) : nullptr;
+  constexpr int total4 = CT_ROWS * SZ / 4;
+  double primal = 0.0, dual = 0.0;
+  for (int q = threadIdx.x; q < total4; q += ADMM_THREADS) {
+    const float4 xv = x4[q], zo = z4[q], uv = u4[q];
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, zs[4] = {zo.x, zo.y, zo.z, zo.w}, us[4] = {uv.x, uv.y, uv.z, uv.w};
+    float zn[4], un[4];
+    bool any_shared = false;
+    if (MAXA > 0) {
+      float add[4][MAXA > 0 ? MAXA : 1];
+      int rr[4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int e = 4 * q + c4, r = e / SZ, c = e - r * SZ;
+        rr[c4] = r;
+        const bool sh = s_sr[r] >= 0;
+        any_shared |= sh;
+#pragma unroll
+        for (int j = 0; j < MAXA; j++) {
+          const uint32_t en = (sh && j < max_addends) ? s_ent[r * max_addends + j] : ENT_NONE;
+          const uint32_t which = en >> 28;
+          add[c4][j] = (en == ENT_NONE || which == 15u)
+                           ? 0.f
+                           : __ldg(a.src[which] + (int64_t)(en & 0x0fffffffu) * ADMM_ROW + row_off + c);
+        }
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int r = rr[c4];
+        const bool sh = s_sr[r] >= 0;
+        const int cnt_i = sh ? (int)s_cnt[r] : 1;
+        float z_new = xs[c4], u_new = us[c4];
+        if (sh) {
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < MAXA; j++) {
+            const uint32_t en = j < max_addends ? s_ent[r * max_addends + j] : ENT_NONE;
+            if (en != ENT_NONE) {                 // (entries are packed: nothing follows the first empty one)
+              const float v = (en >> 28) == 15u ? xs[c4] : add[c4][j];
+              sum = j == 0 ? v : __fadd_rn(sum, v);
+            }
+          }
+          z_new = __fdiv_rn(sum, (float)cnt_i);
+          u_new = __fadd_rn(us[c4], __fmul_rn(relax, __fsub_rn(xs[c4], z_new)));
+        }
+        zn[c4] = z_new; un[c4] = u_new;
+        const double dp = (double)z_new - (double)xs[c4], dd = (double)zs[c4] - (double)z_new;
+        primal += dp * dp;
+        dual += dd * dd * inv_cnt[cnt_i];
+      }
+    } else {
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int e = 4 * q + c4, r = e / SZ, c = e - r * SZ;
+        const int32_t sr = s_sr[r];
+        any_shared |= sr >= 0;
+        consensus_element(a, row_off, c, sr, sr >= 0 ? (int)s_cnt[r] : 1, s_ent + r * max_addends, max_addends, relax,
+                          xs[c4], zs[c4], us[c4], inv_cnt, zn[c4], un[c4], primal, dual);
+      }
+    }
+    z4[q] = make_float4(zn[0], zn[1], zn[2], zn[3]);
+    if (any_shared) u4[q] = make_float4(un[0], un[1], un[2], un[3]);     // single owners: u is unchanged
+    if (has_zmu) m4[q] = make_float4(zn[0] - un[0], zn[1] - un[1], zn[2] - un[2], zn[3] - un[3]);
+  }
+  // per-thread, per-group running sums live in shared memory between tiles (12 doubles per thread would cost
+  // 24 registers of a kernel that needs its occupancy)
+  s_acc[g * ADMM_THREADS + threadIdx.x] += primal;
+  s_acc[(6 + g) * ADMM_THREADS + threadIdx.x] += dual;
+}
+
 template <int MAXA>
-__global__ void __launch_bounds__(ADMM_THREADS)
+__global__ void __launch_bounds__(ADMM_THREADS, CT_MIN_CTAS)
 admm_consensus_kernel(const __grid_constant__ ConsensusArgs a, const int32_t* __restrict__ shared_row,
                       const uint32_t* __restrict__ addends, const uint8_t* __restrict__ count, int max_addends,
                       int64_t n, float relax, double* __restrict__ partial, unsigned int* __restrict__ ticket,
                       double* __restrict__ residuals) {
-  __shared__ double acc[12];
-  __shared__ double inv_cnt[ADMM_THREADS];     // 1 / count without a double division per element
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_acc = reinterpret_cast<double*>(smem_raw);                                  // [12][ADMM_THREADS]
+  uint32_t* s_ent = reinterpret_cast<uint32_t*>(smem_raw + 12 * ADMM_THREADS * sizeof(double));   // [CT_ROWS][max_addends]
+  __shared__ int32_t s_sr[CT_ROWS];
+  __shared__ uint8_t s_cnt[CT_ROWS];
+  __shared__ double inv_cnt[256];              // 1 / count without a double division per element
   __shared__ bool last;
-  if (threadIdx.x < 12) acc[threadIdx.x] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 12; q++) s_acc[q * ADMM_THREADS + threadIdx.x] = 0.0;
   inv_cnt[threadIdx.x] = 1.0 / (double)max((int)threadIdx.x, 1);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const RowLane rl = row_lane(lane);
   const bool has_zmu = a.zmu[0] != nullptr;
-  double primal[2] = {0.0, 0.0}, dual[2] = {0.0, 0.0};
-  const int64_t nwarps = (int64_t)gridDim.x * (ADMM_THREADS / 32);
-  for (int64_t i = (int64_t)blockIdx.x * (ADMM_THREADS / 32) + (threadIdx.x >> 5); i < n; i += nwarps) {
-    const int32_t sr = shared_row[i];
-    int cnt_i = 1;
-    uint32_t ent[MAXA > 0 ? MAXA : 1];
-    if (sr >= 0) {
-      cnt_i = count[sr];
-      if (MAXA > 0) {
-#pragma unroll
-        for (int j = 0; j < MAXA; j++) ent[j] = j < max_addends ? addends[(int64_t)sr * max_addends + j] : 0xffffffffu;
-      }
+  const int64_t ntiles = (n + CT_ROWS - 1) / CT_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t i0 = tile * CT_ROWS;
+    const int rows = (int)min((int64_t)CT_ROWS, n - i0);
+    __syncthreads();                           // the previous tile is done with the tables (and inv_cnt is set)
+    if ((int)threadIdx.x < rows) {
+      const int32_t sr = shared_row[i0 + threadIdx.x];
+      s_sr[threadIdx.x] = sr;
+      s_cnt[threadIdx.x] = sr >= 0 ? count[sr] : (uint8_t)1;
+      const uint32_t* src = addends + (int64_t)(sr >= 0 ? sr : 0) * max_addends;
+      for (int j = 0; j < max_addends; j++) s_ent[threadIdx.x * max_addends + j] = sr >= 0 ? src[j] : ENT_NONE;
     }
-    const float cnt = (float)cnt_i;
-    const double w = inv_cnt[cnt_i];
-    float xv[2], z_old[2], u_val[2], add[2][MAXA > 0 ? MAXA : 1];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (rl.g[h] < 0) continue;
-      const int64_t e = i * rl.sz[h] + rl.off[h];
-      xv[h] = a.x[rl.g[h]][e];
-      z_old[h] = a.z[rl.g[h]][e];
-      u_val[h] = a.u[rl.g[h]][e];
-      if (MAXA > 0 && sr >= 0) {
-#pragma unroll
-        for (int j = 0; j < MAXA; j++) {
-          const uint32_t which = ent[j] >> 28;
-          add[h][j] = (ent[j] == 0xffffffffu || which == 15u)
-                          ? 0.f
-                          : __ldg(a.src[which] + (int64_t)(ent[j] & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
-        }
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (rl.g[h] < 0) continue;
-      const int g = rl.g[h];
-      const int64_t e = i * rl.sz[h] + rl.off[h];
-      float u_new = u_val[h];
-      float z_new = xv[h];
-      if (sr >= 0) {
-        float s = 0.f;
-        if (MAXA > 0) {
-#pragma unroll
-          for (int j = 0; j < MAXA; j++) {
-            if (ent[j] == 0xffffffffu) break;
-            const float v = (ent[j] >> 28) == 15u ? xv[h] : add[h][j];
-            s = j == 0 ? v : __fadd_rn(s, v);
-          }
-        } else {
-          for (int j = 0; j < max_addends; j++) {
-            const uint32_t en = addends[(int64_t)sr * max_addends + j];
-            if (en == 0xffffffffu) break;
-            const uint32_t which = en >> 28;
-            const float v = which == 15u ? xv[h]
-                                         : __ldg(a.src[which] + (int64_t)(en & 0x0fffffffu) * ADMM_ROW + lane + 32 * h);
-            s = j == 0 ? v : __fadd_rn(s, v);
-          }
-        }
-        z_new = __fdiv_rn(s, cnt);
-        u_new = __fadd_rn(u_new, __fmul_rn(relax, __fsub_rn(xv[h], z_new)));
-        a.u[g][e] = u_new;
-      }
-      a.z[g][e] = z_new;
-      if (has_zmu) a.zmu[g][e] = z_new - u_new;
-      const double dp = (double)z_new - (double)xv[h], dd = (double)z_old[h] - (double)z_new;
-      primal[h] += dp * dp;
-      dual[h] += dd * dd * w;
+    __syncthreads();
+    if (rows == CT_ROWS) {
+      consensus_group<3, MAXA>(a, 0, 0, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group<3, MAXA>(a, 1, 3, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group<45, MAXA>(a, 2, 6, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group<3, MAXA>(a, 3, 51, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group<4, MAXA>(a, 4, 54, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group<1, MAXA>(a, 5, 58, i0, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+    } else {      // the last, partial tile: element by element
+      consensus_group_tail<3>(a, 0, 0, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group_tail<3>(a, 1, 3, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group_tail<45>(a, 2, 6, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group_tail<3>(a, 3, 51, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group_tail<4>(a, 4, 54, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
+      consensus_group_tail<1>(a, 5, 58, i0, rows, s_sr, s_cnt, s_ent, max_addends, relax, has_zmu, inv_cnt, s_acc);
     }
   }
+  __syncthreads();
+  // fold the per-thread sums: warp w reduces sums w, w + 8 (12 sums, 8 warps)
+  __shared__ double acc[12];
+  for (int q = threadIdx.x >> 5; q < 12; q += ADMM_THREADS / 32) {
+    double v = 0.0;
+    for (int t = threadIdx.x & 31; t < ADMM_THREADS; t += 32) v += s_acc[q * ADMM_THREADS + t];
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    if (rl.g[h] < 0) continue;
-    if (primal[h] != 0.0) atomicAdd(&acc[rl.g[h]], primal[h]);
-    if (dual[h] != 0.0) atomicAdd(&acc[6 + rl.g[h]], dual[h]);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) acc[q] = v;
   }
   __syncthreads();
   if (threadIdx.x < 12) partial[(size_t)blockIdx.x * 12 + threadIdx.x] = acc[threadIdx.x];
@@ -344,12 +457,16 @@ extern "C" int admm_consensus_update(const AdmmConstTensors* x, const AdmmTensor
   for (int k = 0; k < ADMM_MAX_SOURCES; k++) a.src[k] = (sources && k < n_sources) ? sources[k] : nullptr;
   double* partial = reinterpret_cast<double*>(scratch);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(scratch) + (size_t)(148 * 8) * 12 * sizeof(double));
+  const int64_t ntiles = (n + CT_ROWS - 1) / CT_ROWS;
+  const int grid = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+  const size_t smem = 12 * ADMM_THREADS * sizeof(double) + (size_t)CT_ROWS * (max_addends > 0 ? max_addends : 1) * sizeof(uint32_t);
+  if (max_addends > 16) { set_error("admm_consensus_update: more than 16 addends per Gaussian"); return 1; }
   if (max_addends <= 4)
-    admm_consensus_kernel<4><<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
-                                                                       relax, partial, ticket, residuals);
+    admm_consensus_kernel<4><<<grid, ADMM_THREADS, smem, s>>>(a, shared_row, addends, count, max_addends, n, relax, partial,
+                                                             ticket, residuals);
   else
-    admm_consensus_kernel<0><<<consensus_grid(n), ADMM_THREADS, 0, s>>>(a, shared_row, addends, count, max_addends, n,
-                                                                       relax, partial, ticket, residuals);
+    admm_consensus_kernel<0><<<grid, ADMM_THREADS, smem, s>>>(a, shared_row, addends, count, max_addends, n, relax, partial,
+                                                             ticket, residuals);
   return check_launch("admm_consensus_update", false, s);
 }
 
