@@ -267,7 +267,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const float Tk = T[k];
         const float weight = alpha * Tk;
         const float om = 1.0f - alpha;
-        const float inv = __fdividef(1.0f, om);   // MUFU.RCP (<= 1 ulp): gradients carry a 1e-4 bar
+        // om is in [0.01, 1]: one MUFU.RCP (<= 1 ulp; gradients carry a 1e-4 bar).  __fdividef(1, om) wraps the
+        // same instruction in a range fix-up for huge divisors (7 instructions, 7 % of this kernel).
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(om));
         S[k] += weight * cd;
         const float dL_dalpha = c ? (cd * Tk + inv * S[k]) : 0.f;
         T[k] = Tk * om;
