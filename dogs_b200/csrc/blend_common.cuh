@@ -22,6 +22,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // lies inside, otherwise on an edge facing the mean), compared with thr = ln(255*opacity) plus a
 // margin that dwarfs the rounding error — so a skipped entry has alpha < 1/255 at every pixel of
 // the block and skipping it cannot change any result.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float quad_form(float a, float b, float c, float dx, float dy) {
   return 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy;
 }
@@ -33,8 +38,10 @@ __device__ __forceinline__ bool block_reachable(const float4 co, float mx, float
   const float cxp = fminf(fmaxf(mx, x0), x1), cyp = fminf(fmaxf(my, y0), y1);
   const float ex = cxp - mx, ey = cyp - my;          // 0 when the mean is inside that range
   // vertical facing edge x = cxp: minimise over y;  horizontal facing edge y = cyp: minimise over x
-  const float dyv = fminf(fmaxf(my - co.y * ex * __frcp_rn(co.z), y0), y1) - my;
-  const float dxh = fminf(fmaxf(mx - co.y * ey * __frcp_rn(co.x), x0), x1) - mx;
+  // (approximate reciprocals: an error in the position of the edge minimum changes the value found there
+  //  only in second order, far inside the margin below; the IEEE-rounded __frcp_rn was 45 % of this test)
+  const float dyv = fminf(fmaxf(my - co.y * ex * rcp_approx(co.z), y0), y1) - my;
+  const float dxh = fminf(fmaxf(mx - co.y * ey * rcp_approx(co.x), x0), x1) - mx;
   const float qv = quad_form(co.x, co.y, co.z, ex, dyv);
   const float qh = quad_form(co.x, co.y, co.z, dxh, ey);
   // mean inside the x range: only the horizontal edge counts (and vice versa); inside both: 0
