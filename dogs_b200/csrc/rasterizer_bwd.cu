@@ -472,41 +472,58 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     if (bulk) mbar_wait(&sh_bar, 0);       // threads beyond P: nobody passes while the copy may still be in flight
     float* dst = dL_dsh + (size_t)first * 3 * M;
     const bool pen = admm.zmu_sh != nullptr;
-    const bool bulk_out = !pen && (((uintptr_t)dst) & 15) == 0 && ((nfl * sizeof(float)) & 15) == 0;
+    if (pen) {
+      // ADMM penalty of the SH coefficients, added to the staged gradient slice in place: x is re-read (L2: this
+      // CTA just loaded it), z - u comes from HBM.  Four 16-byte vectors per thread and array are requested before
+      // the first one is used: the rolled loop of the first version waited for memory 11 times per CTA and made
+      // this kernel 0.26 ms slower with the penalty than without (0.11 ms of it is the extra traffic).
+      __syncthreads();                     // every thread's gradient row is in the slice
+      const float* xs = shs + (size_t)first * 3 * M;
+      const float* zs = admm.zmu_sh + (size_t)first * 3 * M;
+      const bool al16 = ((((uintptr_t)xs) | ((uintptr_t)zs)) & 15) == 0;
+      const size_t n4 = al16 ? nfl >> 2 : 0;
+      const float4* x4 = reinterpret_cast<const float4*>(xs);
+      const float4* z4 = reinterpret_cast<const float4*>(zs);
+      float acc = 0.f;
+      for (size_t base = 0; base < n4; base += PREB_THREADS * 4) {
+        float4 xv[4], zv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const size_t i = base + k * PREB_THREADS + threadIdx.x;
+          if (i < n4) { xv[k] = __ldg(x4 + i); zv[k] = __ldg(z4 + i); }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const size_t i = base + k * PREB_THREADS + threadIdx.x;
+          if (i < n4) {
+            float4 g = stage4[i];
+            const float r0 = xv[k].x - zv[k].x, r1 = xv[k].y - zv[k].y, r2 = xv[k].z - zv[k].z, r3 = xv[k].w - zv[k].w;
+            g.x += admm.coef_sh * r0; g.y += admm.coef_sh * r1; g.z += admm.coef_sh * r2; g.w += admm.coef_sh * r3;
+            acc += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+            stage4[i] = g;
+          }
+        }
+        pen_sh += (double)acc;             // <= 16 squares per step in float, everything above in double
+        acc = 0.f;
+      }
+      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) {
+        const float r = xs[i] - zs[i];
+        stage[i] += admm.coef_sh * r;
+        pen_sh += (double)(r * r);
+      }
+    }
+    const bool bulk_out = (((uintptr_t)dst) & 15) == 0 && ((nfl * sizeof(float)) & 15) == 0;
     if (bulk_out) fence_smem_to_async();
     __syncthreads();
     if (bulk_out) {
       if (threadIdx.x == 0) bulk_store_and_wait(dst, stage, (uint32_t)(nfl * sizeof(float)));
-    } else {
-    const float* xs = shs + (size_t)first * 3 * M;            // still L2-resident: this CTA just read it
-    const float* zs = pen ? admm.zmu_sh + (size_t)first * 3 * M : nullptr;
-    const bool al16 = ((((uintptr_t)dst) | ((uintptr_t)xs) | ((uintptr_t)zs)) & 15) == 0;
-    if (al16) {
+    } else if ((((uintptr_t)dst) & 15) == 0) {
       float4* dst4 = reinterpret_cast<float4*>(dst);
       const size_t n4 = nfl >> 2;
-      for (size_t i = threadIdx.x; i < n4; i += PREB_THREADS) {
-        float4 g = stage4[i];
-        if (pen) {
-          const float4 xv = __ldg(reinterpret_cast<const float4*>(xs) + i);
-          const float4 zv = __ldg(reinterpret_cast<const float4*>(zs) + i);
-          const float r0 = xv.x - zv.x, r1 = xv.y - zv.y, r2 = xv.z - zv.z, r3 = xv.w - zv.w;
-          g.x += admm.coef_sh * r0; g.y += admm.coef_sh * r1; g.z += admm.coef_sh * r2; g.w += admm.coef_sh * r3;
-          pen_sh += (double)(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
-        }
-        dst4[i] = g;
-      }
-      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) {
-        float g = stage[i];
-        if (pen) { const float r = xs[i] - zs[i]; g += admm.coef_sh * r; pen_sh += (double)(r * r); }
-        dst[i] = g;
-      }
+      for (size_t i = threadIdx.x; i < n4; i += PREB_THREADS) dst4[i] = stage4[i];
+      for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) dst[i] = stage[i];
     } else {
-      for (size_t i = threadIdx.x; i < nfl; i += PREB_THREADS) {
-        float g = stage[i];
-        if (pen) { const float r = xs[i] - zs[i]; g += admm.coef_sh * r; pen_sh += (double)(r * r); }
-        dst[i] = g;
-      }
-    }
+      for (size_t i = threadIdx.x; i < nfl; i += PREB_THREADS) dst[i] = stage[i];
     }
   }
   if (pen_partial) {
