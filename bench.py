@@ -288,7 +288,30 @@ def timed_steps(step, K, barrier, after=None):
     return ev0, ev1, marks
 
 
-def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed):
+def admm_cpu_baseline(gidx, n_global, blocks=(0, 1)):
+    """CPU baseline of the consensus round: the reference's master / slave arithmetic — scatter-add
+    of every owner's 59 parameters, division by the owner count, dual update (master_gaussian_trainer.py:538-555,
+    slave_gaussian_trainer.py:99-121) — as restated in oracle/oracle.py (numpy, one core), on a bounded sample of
+    the C4 blocks, scaled to all eight."""
+    import numpy as np
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    idx = [gidx[b].numpy() for b in blocks]
+    xs = [[rng.standard_normal((len(i), sz), dtype=np.float32) for sz in O.GROUP_SIZES] for i in idx]
+    us = [[np.zeros_like(a) for a in x] for x in xs]
+    t0 = time.perf_counter()
+    with np.errstate(invalid="ignore", divide="ignore"):     # Gaussians of the blocks outside the sample have no owner
+        z, _ = O.admm_consensus(xs, idx, n_global)
+    for x, u, i in zip(xs, us, idx):
+        O.admm_dual_update(x, u, [zg[i] for zg in z])
+    dt = time.perf_counter() - t0
+    est = dt * 8.0 / len(blocks)
+    return {"value": 1.0 / est, "unit": "consensus rounds/s", "cores": 1, "kind": "port",
+            "sample": f"{len(blocks)} of 8 blocks ({sum(len(i) for i in idx)} Gaussians): scatter-add, average, dual update "
+                      f"in numpy ({dt:.1f} s), scaled x{8 // len(blocks)}", "est_s_per_round": est}
+
+
+def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed, cpu_baseline_leg=False):
     """8 blocks (C4: 2 M, C5: 4 M Gaussians each), 4 x 2 grid, x1.4 expansion, time-sliced over
     the ranks.  One ADMM iteration = every block runs one training step (render of its own camera with the
     fused penalty, loss, backward); one consensus round closes the timed region."""
@@ -371,6 +394,12 @@ def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed):
                                                                  "recv_buffer": int(topo.recv_rows_total) * 236},
            "hbm_gb_rank0": torch.cuda.max_memory_allocated(dev) / 1e9,
            "exchange": check if check is not None else {"transport": "none: all blocks on one GPU read each other's send rows in place"}}
+    if cpu_baseline_leg and rank == 0:
+        try:
+            out["cpu_baseline"] = admm_cpu_baseline(gidx, n_global)
+            out["cpu_baseline"]["gpu_rounds_per_s"] = 1e3 / round_ms
+        except Exception as ex:  # pylint: disable=W0703
+            out["cpu_baseline"] = {"error": repr(ex)}
     del grp, models
     torch.cuda.empty_cache()
     return out
@@ -635,7 +664,8 @@ def main():
     admm_obj = None
     if ours and not args.no_admm and not args.force_admm:
         try:
-            admm_obj = admm_protocol("C4", dgr, loss_of, max(K // 2, 5), 3, rank, world, dev, distributed)
+            admm_obj = admm_protocol("C4", dgr, loss_of, max(K // 2, 5), 3, rank, world, dev, distributed,
+                                     cpu_baseline_leg=(world == 1 and not args.no_cpu_baseline))
         except Exception as ex:  # pylint: disable=W0703
             admm_obj = {"error": repr(ex)}
 
