@@ -53,8 +53,10 @@ def test_fused_ssim_golden_and_oracle():
     assert np.abs(om - m.cpu().numpy()).max() <= 2e-6
 
 
-@pytest.mark.parametrize("P", [100_000, 4097, 1024, 5, 3])
+@pytest.mark.parametrize("P", [1_100_000, 100_000, 4097, 1024, 5, 3])
 def test_simple_knn_bit_exact(P):
+    # (1.1 M points: Morton sort of more than 2^20 keys = the three-kernel radix passes; the smaller sizes run the
+    #  chained single-kernel passes, csrc/radix_sort.cu)
     _, _, rknn = _ref()
     from dogs_b200.simple_knn._C import distCUDA2
     g = torch.Generator(device="cpu").manual_seed(P)
