@@ -113,7 +113,8 @@ typedef struct DgrForwardInfo {
  * exactly one of (scales+rotations | cov3D_precomp).
  *   out_color [3,H,W], out_invdepth [1,H,W], radii [P] are caller-allocated (need not be zeroed).
  *   geom/binning/image callbacks allocate the state kept for backward; scratch may be freed
- *   as soon as the call returns (stream-ordered). */
+ *   as soon as the call returns (stream-ordered).  Every buffer a callback hands out must stay valid until
+ *   the call returns (the scratch callback is invoked more than once per call). */
 int dgr_forward(const DgrParams* prm,
                 const float* means3D, const float* dc, const float* sh,
                 const float* colors_precomp, const float* opacities,
@@ -168,7 +169,7 @@ typedef struct DgrLayout {
   size_t geom_bytes;
   size_t bin_point_list;   /* uint32[R] Gaussian id per sorted instance                */
   size_t bin_tile_keys;    /* uint32[R] tile id per sorted instance                    */
-  size_t bin_bytes;
+  size_t bin_bytes;        /* (+ the forward's sub-tile reachability words read by the backward: ~1 byte per instance) */
   size_t img_ranges;       /* uint2[T]                                                 */
   size_t img_final_T;      /* float[N]                                                 */
   size_t img_n_contrib;    /* uint32[N]                                                */
