@@ -349,6 +349,42 @@ def test_mixed_rect_sizes_vs_reference(P):
         assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, k
 
 
+@pytest.mark.parametrize("L", [1, 63, 64, 65, 127, 128, 129, 255, 256, 257, 600])
+def test_blend_batch_boundaries_vs_reference(L):
+    """Tile lists of exactly L entries around the staging batch sizes (64 records per round in blend_bwd, 256 in
+    blend_fwd, 32 per reachability word), every entry a faint Gaussian as large as the 2 x 2 tile image: it reaches
+    all eight 8x4 blocks of every tile, nothing saturates, so every entry is blended by every pixel and both half
+    tiles store totals for every entry of every round (the per-warp sAcc / sWritten protocol and the reuse of the
+    forward's reachability words)."""
+    dgr = _need_ref()
+    spec = scenes.SPECS["tiny"]._replace(W=32, H=32)
+    sc = scenes.make_scene(spec, 31, DEV, P=L)
+    g = torch.Generator(device="cpu").manual_seed(100 + L)
+    # centres within a few pixels of the image centre, sigma ~ 21 px (3 sigma covers the frame), opacity 0.01-0.02
+    sc["means3D"] = (torch.randn(L, 3, generator=g) * 0.1).to(DEV).contiguous()
+    sc["scales"] = torch.full((L, 3), 0.6, device=DEV) * (1.0 + 0.2 * torch.rand(L, 3, generator=g).to(DEV))
+    sc["opacities"] = (0.01 + 0.01 * torch.rand(L, 1, generator=g)).to(DEV)
+    r = U.ref_forward_raw(dgr, sc)
+    o = U.ours_forward_raw(sc)
+    H, W = sc["H"], sc["W"]
+    ri = U.parse_ref_image(r["img"], H * W)
+    assert torch.equal(r["radii"], o["radii"])
+    assert torch.equal(ri["n_contrib"], o["n_contrib"])
+    assert torch.equal(U.bits(ri["accum_alpha"]), U.bits(o["final_T"]))
+    assert (r["color"] - o["color"]).abs().max().item() <= IMG_TOL
+    vis = int((o["radii"] > 0).sum())
+    if vis:    # the construction really exercises full lists: (nearly) every visible Gaussian is in all four tiles
+        assert int(o["num_rendered"]) >= 3 * vis
+        assert int(o["n_contrib"].max()) >= min(vis, L) - 2
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
+    dLc, dLd = _out_grads(sc)
+    gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+    go = U.ours_backward(sc, dLc, dLd)
+    for k in GRAD_KEYS:
+        assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, k
+
+
 @pytest.mark.parametrize("cfg", ["C2", "C3"])
 def test_full_size_properties(cfg):
     """BASELINE.json's headline size: exact forward parity with the reference plus
