@@ -635,6 +635,28 @@ def main():
                        "gaussians": s2["means3D"].shape[0], "image": [s2["W"], s2["H"]]}
             del m2, s2, t2
         extra["configs"] = cfgs
+        # the same steps replayed as one CUDA graph each (dogs_b200.graphs.GraphedStep: forward in the library's
+        # deferred-check mode, verified after every replay): what is left when the host no longer paces the step
+        if ours:
+            try:
+                from dogs_b200.graphs import GraphedStep
+                gcfg = {}
+                for c in ("C1", "C2"):
+                    s2 = scenes.make_scene(c, seed=0, device=dev)
+                    t2 = torch.rand(3, s2["H"], s2["W"], device=dev)
+                    m2 = Trainee(dgr, loss_of, s2, t2)
+                    gs = GraphedStep(m2.step, warmup=Wm)
+                    for _ in range(2):
+                        gs()
+                    e0, e1, mk = timed_steps(gs, K, barrier)
+                    barrier()
+                    gcfg[c] = {"value": K / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / K,
+                               "recaptures": gs.recaptures}
+                    del gs, m2, s2, t2
+                extra["graphed"] = gcfg
+            except Exception as ex:  # pylint: disable=W0703
+                extra["graphed"] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
         # the same C3 step followed by the sparse Adam update of all six tensors (SURVEY.md 8f.1,
         # gaussian_trainer.py:474-476): six adamUpdate launches in the reference, one here
         mo = Trainee(dgr, loss_of, sc, target, optimizer=True)

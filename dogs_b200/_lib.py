@@ -34,6 +34,7 @@ class DgrParams(C.Structure):
         ("admm", C.POINTER(DgrAdmmPenalty)),
         ("gaussians_count", C.c_void_p), ("important_score", C.c_void_p),
         ("instance_capacity", C.c_int32), ("depth_key_bits", C.c_int32),
+        ("deferred_check", C.c_void_p),
     ]
 
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "dgr_mark_visible": [C.c_int32, _P, _P, _P, _P, _P],
     "dgr_apply_activations": [C.c_int32, _P, _P, _P, _P, _P, _P, _P],
     "dgr_layout": [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DgrLayout)],
+    "dgr_deferred_check": [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "dgr_sparse_adam": [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
                         C.c_uint32, C.c_uint32, _P],
     "dgr_sparse_adam_multi": [C.POINTER(DgrAdamTensor), C.c_int32, _P, _P, C.c_float, C.c_float, C.c_uint32, _P],

@@ -188,6 +188,16 @@ int dgr_layout(int32_t P, int32_t W, int32_t H, int32_t R, DgrLayout* out) {
   return 0;
 }
 
+int dgr_deferred_check(const uint32_t* words, int32_t instance_capacity, int32_t depth_key_bits,
+                       int32_t* num_rendered, int32_t* key_bits) {
+  if (!words) return 0;
+  const int kb = significant_key_bits(words[0], words[1]);
+  if (num_rendered) *num_rendered = (int32_t)words[2];
+  if (key_bits) *key_bits = kb;
+  const int assumed = (depth_key_bits >= 1 && depth_key_bits <= 32) ? depth_key_bits : 32;
+  return (words[2] <= (uint32_t)instance_capacity && kb <= assumed) ? 1 : 0;
+}
+
 int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, const float* sh,
                 const float* colors_precomp, const float* opacities, const float* scales,
                 const float* rotations, const float* cov3D_precomp, float* out_color,
@@ -238,8 +248,11 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
   int key_bits = 0;
   size_t scratch1_bytes = 0, scratch2_bytes = 0;
   StageClock clk(g_stage_timing, s);
-  HostReadback* rb = readback();
-  if (!rb) { set_error("forward: cannot create the pinned read-back slot"); return 1; }
+  // deferred mode (DgrParams::deferred_check): nothing below waits for the device or touches a second stream
+  const bool deferred = p.deferred_check != nullptr;
+  if (deferred && p.instance_capacity <= 0) { set_error("forward: deferred_check needs instance_capacity > 0"); return 1; }
+  HostReadback* rb = deferred ? nullptr : readback();
+  if (!deferred && !rb) { set_error("forward: cannot create the pinned read-back slot"); return 1; }
   const int bits = higher_msb((uint32_t)T);
   const int passes = (bits + 7) / 8;
   BinState b = BinState::carve(nullptr, 0, T);
@@ -311,6 +324,26 @@ int dgr_forward(const DgrParams* prm, const float* means3D, const float* dc, con
     };
     const int bits_assumed = (p.depth_key_bits >= 1 && p.depth_key_bits <= 32) ? p.depth_key_bits : 32;
     if (depth_stage(bits_assumed)) return 1;
+    if (deferred) {
+      clk.mark();   // [2] gather + scan
+      if (bin_and_blend((uint32_t)p.instance_capacity, true)) return 1;
+      if (cudaMemcpyAsync(p.deferred_check, g.ctl, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+        set_error("[CUDA ERROR] deferred_check copy: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+      }
+      clk.finish(g_fwd_stage_ms, &g_fwd_stage_n);
+      if (info) {
+        info->num_rendered = -1;
+        info->num_visible = -1;
+        info->binning_rows = (int32_t)rows;
+        info->depth_key_bits = bits_assumed;
+        info->geom_bytes = geom_bytes;
+        info->binning_bytes = bin_bytes;
+        info->image_bytes = img_bytes;
+        info->scratch_bytes = scratch1_bytes > scratch2_bytes ? scratch1_bytes : scratch2_bytes;
+      }
+      return 0;
+    }
     // {smallest key, largest key, R} -> pinned host memory on the side stream
     cudaError_t e = cudaEventRecord(rb->ev_ready, s);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(rb->side, rb->ev_ready, 0);

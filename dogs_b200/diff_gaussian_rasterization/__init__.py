@@ -79,6 +79,52 @@ def _learn_capacity(device, info):
     _DEPTH_KEY_BITS[k] = max(_DEPTH_KEY_BITS.get(k, 0), int(info.depth_key_bits))
 
 
+# ---- deferred checks: forward calls recorded into a CUDA graph ----------------------------------------------------
+# While the current stream is being captured the forward cannot wait for the instance count, so it runs in the
+# library's deferred mode (DgrParams::deferred_check): the capacity and the depth-key bits learnt by earlier eager
+# calls are taken for granted, the measured values land in pinned memory in stream order, and whoever replays the
+# graph verifies them afterwards (dogs_b200.graphs.GraphedStep does).
+class DeferredChecks:
+    """Pinned slots for the forwards recorded during one capture + what each of them assumed."""
+
+    def __init__(self, slots: int = 16):
+        self.words = torch.zeros(slots, 4, dtype=torch.int32).pin_memory()
+        self.entries = []          # (device index, slot, capacity, key bits)
+
+    def take(self, device_index, capacity, key_bits):
+        slot = len(self.entries)
+        if slot >= self.words.shape[0]:
+            raise RuntimeError("more rasterizer forwards in one captured step than DeferredChecks has slots")
+        self.entries.append((device_index, slot, int(capacity), int(key_bits)))
+        return self.words[slot].data_ptr()
+
+    def ok(self):
+        """After the replayed work has completed: did every recorded forward stay within what it assumed?
+        Whatever the answer, the measured instance counts / key bits update the learnt capacity."""
+        good = True
+        for dev, slot, cap, bits in self.entries:
+            r, kb = C.c_int32(0), C.c_int32(0)
+            good &= bool(L.lib().dgr_deferred_check(self.words[slot].data_ptr(), cap, bits, C.byref(r), C.byref(kb)))
+            _INSTANCE_CAPACITY[dev] = max(_INSTANCE_CAPACITY.get(dev, 0), int(r.value * 1.25) + 4096)
+            _DEPTH_KEY_BITS[dev] = max(_DEPTH_KEY_BITS.get(dev, 0), int(kb.value))
+        return good
+
+
+_RECORDER = None
+
+
+def begin_deferred_checks(slots: int = 16) -> DeferredChecks:
+    """Call right before capturing (torch.cuda.graph) a step that contains rasterizer forwards."""
+    global _RECORDER
+    _RECORDER = DeferredChecks(slots)
+    return _RECORDER
+
+
+def end_deferred_checks():
+    global _RECORDER
+    _RECORDER = None
+
+
 def _params(rs, P, M, device, backward=False):
     f = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
     keep = (f(rs.bg), f(rs.viewmatrix), f(rs.projmatrix), f(rs.campos))
@@ -186,6 +232,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             prm, keep = _params(rs, P, M, device)
             prm.instance_capacity = _capacity_for(device)
             prm.depth_key_bits = _DEPTH_KEY_BITS.get(device.index or 0, 0)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                if _RECORDER is None:
+                    raise RuntimeError("rasterizer forward inside a CUDA-graph capture: call begin_deferred_checks() first "
+                                       "(dogs_b200.graphs.GraphedStep does all of this)")
+                cap = _INSTANCE_CAPACITY.get(device.index or 0, 0)
+                if cap <= 0:
+                    raise RuntimeError("run the step eagerly at least once before capturing it (the instance capacity "
+                                       "and the depth-key bits are learnt from eager calls)")
+                prm.instance_capacity = cap
+                prm.deferred_check = _RECORDER.take(device.index or 0, cap, prm.depth_key_bits)
             info = L.DgrForwardInfo()
             with torch.cuda.device(device):
                 args = (C.byref(prm), L.ptr(means3D), L.ptr(dc), L.ptr(sh), L.ptr(colors_precomp),
@@ -205,7 +262,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 else:
                     L.check(L.lib().dgr_forward(*args))
             num_rendered = info.binning_rows    # the row count the binning buffer is carved with
-            _learn_capacity(device, info)
+            if not capturing:
+                _learn_capacity(device, info)
             scratch.buffers.clear()      # stream-ordered: safe to hand back to the caching allocator now
             del keep
         else:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DOGS_B200_ABI_VERSION 2
+#define DOGS_B200_ABI_VERSION 3
 
 /* Allocation callback: must return a device pointer to >= bytes bytes, aligned to
  * 256 B, valid until the caller decides to free it.  Mirrors resizeFunctional()
@@ -97,6 +97,13 @@ typedef struct DgrParams {
    * earlier frames (their maximum).  The forward verifies it and repeats the depth stage on 32 bits if the
    * range was wider, so the results never depend on this value. */
   int32_t depth_key_bits;
+  /* forward only, nullable: 4 words of PINNED host memory.  With instance_capacity > 0 and this pointer set the
+   * forward does not wait for the device at all — no event, no second stream, so the call can be captured in a
+   * CUDA graph: {smallest depth key, largest depth key, R, 0} are copied to the words in stream order and the
+   * CALLER verifies, once the stream work has completed, that the assumptions held (dgr_deferred_check).  If they
+   * did not, the outputs of that call (and of the backward that used its state) are invalid and the step must be
+   * repeated with a larger capacity / more key bits.  DgrForwardInfo::num_rendered is -1 in this mode. */
+  uint32_t* deferred_check;
 } DgrParams;
 
 /* Sizes / counters reported by dgr_forward (host side). */
@@ -108,6 +115,12 @@ typedef struct DgrForwardInfo {
   int32_t binning_rows;    /* rows the binning buffer was carved for (= num_rendered, or the capacity that was used):
                               pass THIS as `num_rendered` to dgr_backward and dgr_layout */
 } DgrForwardInfo;
+
+/* Verdict on a deferred forward (DgrParams::deferred_check), to be called after the stream work has completed:
+ * returns 1 if R <= instance_capacity and the depth keys differed in at most depth_key_bits bits (0 = 32), else 0.
+ * num_rendered / key_bits (nullable) receive the measured values either way. */
+int dgr_deferred_check(const uint32_t* words, int32_t instance_capacity, int32_t depth_key_bits,
+                       int32_t* num_rendered, int32_t* key_bits);
 
 /* Forward.  Nullable inputs follow the reference: exactly one of (dc+sh | colors_precomp),
  * exactly one of (scales+rotations | cov3D_precomp).

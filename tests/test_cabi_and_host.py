@@ -28,14 +28,15 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/dogs_b200.h but not exported"
     assert set(_lib.SIGNATURES) <= set(names), set(_lib.SIGNATURES) - set(names)
-    assert lib.dogs_abi_version() == 2
+    assert lib.dogs_abi_version() == 3
     assert lib.dogs_last_error() is not None
 
 
 def test_struct_layouts_match_header():
     from dogs_b200 import _lib
     # DgrParams: 5 ints, 4 floats, 3 ints, 4 pointers, 2 ints, 1 pointer, 2 pointers
-    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16 + 8       # + instance_capacity, padded
+    assert C.sizeof(_lib.DgrParams) == 5 * 4 + 4 * 4 + 3 * 4 + 4 * 8 + 8 + 8 + 16 + 8 + 8   # + capacity / key bits, + deferred_check
+    assert _lib.DgrParams.deferred_check.offset == 120
     assert _lib.DgrParams.instance_capacity.offset == 112 and _lib.DgrParams.depth_key_bits.offset == 116
     assert _lib.DgrForwardInfo.depth_key_bits.offset == 40 and _lib.DgrForwardInfo.binning_rows.offset == 44
     assert _lib.DgrParams.bg.offset == 48 and _lib.DgrParams.ref_bucket_cull_quirk.offset == 80
