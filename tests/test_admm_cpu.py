@@ -267,6 +267,6 @@ def test_state_dict_round_trip_with_reference_keys():
 
 def test_cuda_ops_is_the_default_and_needs_the_library():
     ops = A.CudaOps()       # loads libdogs_b200.so (raises ImportError if it was not built)
-    assert ops.lib.dogs_abi_version() == 2
+    assert ops.lib.dogs_abi_version() == 3
     with pytest.raises(RuntimeError, match="contiguous float32 CUDA tensors"):
         ops._t6([torch.zeros(3, 3)] * 6)
