@@ -365,7 +365,8 @@ def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed, cpu
     ev0, ev1, marks = timed_steps(iteration, K, barrier, after=grp.consensus)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    it_ms = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
+    it_seq = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
+    it_ms = sorted(it_seq)
     rounds = []
     for _ in range(3):
         barrier()
@@ -387,7 +388,7 @@ def admm_protocol(cfg, dgr, loss_of, K, warm, rank, world, dev, distributed, cpu
            "penalty": "all 59 parameters, fused into the rasterizer backward, every iteration",
            "iters": K, "consensus_rounds_in_timed_region": 1, "ms_total": ms, "ms_per_iter": ms / K,
            "iters_per_s": K / (ms / 1e3), "block_iters_per_s": nb * K / (ms / 1e3),
-           "iter_ms_rank0": {"min": it_ms[0], "median": it_ms[K // 2], "max": it_ms[-1]},
+           "iter_ms_rank0": {"min": it_ms[0], "median": it_ms[K // 2], "max": it_ms[-1], "in_order": [round(t, 3) for t in it_seq]},
            "consensus_round_ms": round_ms, "consensus_interval_reference": 200,
            "iters_per_s_at_interval_200": 1e3 / (it_ms[K // 2] + round_ms / 200.0),
            "shared_rows_rank0": shared, "exchange_bytes_rank0": {"send_buffer": int(topo.send_rows_total) * 236,
@@ -686,7 +687,7 @@ def main():
     admm_obj = None
     if ours and not args.no_admm and not args.force_admm:
         try:
-            admm_obj = admm_protocol("C4", dgr, loss_of, max(K // 2, 5), 3, rank, world, dev, distributed,
+            admm_obj = admm_protocol("C4", dgr, loss_of, max(K // 2, 5), 6, rank, world, dev, distributed,
                                      cpu_baseline_leg=(world == 1 and not args.no_cpu_baseline))
         except Exception as ex:  # pylint: disable=W0703
             admm_obj = {"error": repr(ex)}
