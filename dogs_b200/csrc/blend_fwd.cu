@@ -36,9 +36,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  float* __restrict__ out_color, float* __restrict__ invdepth,
                  float* __restrict__ pix_color, float* __restrict__ pix_invdepth,
                  int* __restrict__ gaussian_count, uint32_t* __restrict__ hits) {
-  __shared__ float4 sA[2][TILE_PIX];
-  __shared__ float4 sB[2][TILE_PIX];
-  __shared__ float4 sC[2][TILE_PIX];
+  // staged records, one 48-byte struct per entry: the three 16-byte loads of an entry share one address computation
+  __shared__ SplatRecord sR[2][TILE_PIX];
   __shared__ uint32_t sId[COUNT ? 2 : 1][COUNT ? TILE_PIX : 1];
   __shared__ int sCnt[COUNT ? TILE_PIX : 1];
   __shared__ uint32_t sHit[2][TILE_PIX / 32][8];   // [buffer][group of 32 entries][8x4 block = warp]
@@ -75,9 +74,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const uint32_t id = point_list[progress];
       if (COUNT) sId[buf][tid] = id;
       const SplatRecord* r = rec + id;
-      cp_async16(&sA[buf][tid], &r->a);
-      cp_async16(&sB[buf][tid], &r->b);
-      cp_async16(&sC[buf][tid], &r->c);
+      cp_async16(&sR[buf][tid].a, &r->a);
+      cp_async16(&sR[buf][tid].b, &r->b);
+      cp_async16(&sR[buf][tid].c, &r->c);
     }
     cp_async_commit();
   };
@@ -112,8 +111,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const int j = r * 32 + lane;
       bool h = false;
       if (j < nbatch) {
-        const float4 b = sB[buf][j];
-        h = block_reachable(sA[buf][j], b.x, b.y, rx0, ry0, rx1, ry1, sC[buf][j].w);
+        const SplatRecord& e = sR[buf][j];
+        const float4 b = e.b;
+        h = block_reachable(e.a, b.x, b.y, rx0, ry0, rx1, ry1, e.c.w);
       }
       hit[r] = __ballot_sync(0xffffffffu, h);
       if (lane == r) sHit[buf][r][warp] = hit[r];
@@ -129,28 +129,30 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const int j = r * 32 + __ffs(m) - 1;
         m &= m - 1;
         bool blended = false;
-        if (!done) {
-          const float4 con_o = sA[buf][j];
-          const float4 b = sB[buf][j];
+        {
+          // One predicate instead of four nested branches: power, exp and alpha are evaluated by every lane (a lane
+          // that is done, or whose power is positive, computes a value nobody uses), the state changes only under ok.
+          const SplatRecord& e = sR[buf][j];
+          const float4 con_o = e.a;
+          const float4 b = e.b;
           float2 xy = {b.x, b.y};
           float2 d = {xy.x - pixf.x, xy.y - pixf.y};
           float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-          if (!(power > 0.0f)) {
-            float alpha = min(0.99f, con_o.w * exp(power));
-            if (!(alpha < 1.0f / 255.0f)) {
-              float test_T = T * (1 - alpha);
-              if (test_T < 0.0001f) {
-                done = true;
-              } else {
-                const float4 c = sC[buf][j];
-                C[0] += b.w * alpha * T;
-                C[1] += c.x * alpha * T;
-                C[2] += c.y * alpha * T;
-                expected_invdepth += b.z * alpha * T;
-                T = test_T;
-                last_contributor = base + j + 1;   // forward.cu:444,479: position in the tile's list
-                blended = true;
-              }
+          float alpha = min(0.99f, con_o.w * exp(power));
+          const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          if (ok) {
+            float test_T = T * (1 - alpha);
+            if (test_T < 0.0001f) {
+              done = true;
+            } else {
+              const float4 c = e.c;
+              C[0] += b.w * alpha * T;
+              C[1] += c.x * alpha * T;
+              C[2] += c.y * alpha * T;
+              expected_invdepth += b.z * alpha * T;
+              T = test_T;
+              last_contributor = base + j + 1;   // forward.cu:444,479: position in the tile's list
+              blended = true;
             }
           }
         }
