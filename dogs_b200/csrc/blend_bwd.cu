@@ -96,9 +96,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  const float* __restrict__ pixel_colors, const float* __restrict__ pixel_invdepths,
                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_invdepths,
                  float* __restrict__ accum, bool ref_quirk, const uint32_t* __restrict__ hits) {
-  __shared__ float4 sA[2][BB_BATCH];
-  __shared__ float4 sB[2][BB_BATCH];
-  __shared__ float4 sC[2][BB_BATCH];
+  __shared__ SplatRecord sR[2][BB_BATCH];      // one 48-byte struct per entry: one address for its three loads
   __shared__ uint32_t sId[2][BB_BATCH];
   __shared__ __align__(16) uint32_t sHit[2][16];   // [buffer][2 groups of 32 entries x 8 blocks] from the forward pass
   // Per-warp totals of the batch: a warp meets an entry at most once per round, so it simply STORES its
@@ -194,9 +192,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       uint32_t id = point_list[range.x + progress];
       sId[buf][tid] = id;
       const SplatRecord* r = rec + id;
-      bb_cp_async16(&sA[buf][tid], &r->a);
-      bb_cp_async16(&sB[buf][tid], &r->b);
-      bb_cp_async16(&sC[buf][tid], &r->c);
+      bb_cp_async16(&sR[buf][tid].a, &r->a);
+      bb_cp_async16(&sR[buf][tid].b, &r->b);
+      bb_cp_async16(&sR[buf][tid].c, &r->c);
     }
     // the forward's reachability words of these 64 entries: 2 groups x 8 blocks = 64 contiguous bytes
     if (tid < 4) bb_cp_async16(&sHit[buf][4 * tid], hit_in + (size_t)round * 16 + 4 * tid);
@@ -236,9 +234,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const int j = 32 * w + bit;
       const uint32_t e = base + j;
       const uint32_t mk = __shfl_sync(0xffffffffu, bm, bit);   // warp-uniform block mask of entry j
-      const float4 con_o = sA[buf][j];
-      const float4 b = sB[buf][j];
-      const float4 cc = sC[buf][j];
+      const SplatRecord& ent = sR[buf][j];
+      const float4 con_o = ent.a;
+      const float4 b = ent.b;
+      const float4 cc = ent.c;
       const float invd = b.z;
       const float dx = b.x - pxf;
       float v[10];
@@ -308,7 +307,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       for (int q = 0; q < 10; q++) a[q] = (w0 ? sAcc[0][tid][q] : 0.f) + (w1 ? sAcc[1][tid][q] : 0.f);
       if (w0 | w1) {
         // moments -> gradients (backward.cu:626-641):  dL/dG * G = o * q
-        const float4 co = sA[buf][tid];
+        const float4 co = sR[buf][tid].a;
         const float o = co.w;
         const float g_mx = -o * ddelx_dx * a[1];
         const float g_my = -o * ddely_dy * a[2];
