@@ -17,7 +17,7 @@
 #include "blend_common.cuh"
 
 #ifndef BF_MIN_CTAS
-#define BF_MIN_CTAS 8
+#define BF_MIN_CTAS 6
 #endif
 
 namespace dogs {
