@@ -568,6 +568,7 @@ def main():
         consumed = [torch.cuda.Event() for _ in range(2)]
         loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_ev = [torch.cuda.Event() for _ in range(2)]
+        computed = [torch.cuda.Event() for _ in range(2)]
         losses = []
 
         def prefetch(i):
@@ -579,7 +580,7 @@ def main():
                     dev_cam[b][k].copy_(v, non_blocking=True)
                 ready[b].record(copy_stream)
 
-        def e2e_loop(n):
+        def e2e_loop(n, marks=None):
             cur = torch.cuda.current_stream(dev)
             for b in range(2):
                 consumed[b].record(cur)
@@ -593,8 +594,19 @@ def main():
                 scene.update(dev_cam[b])
                 loss = step(scene, dev_target[b])
                 consumed[b].record(cur)
-                loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of this step's loss (4 B)
-                loss_ev[b].record(cur)
+                # D2H of this step's loss (4 B) on the copy stream, so that no copy node sits between two steps
+                # of the compute stream
+                computed[b].record(cur)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(computed[b])
+                    lv = loss.detach().reshape(1)
+                    lv.record_stream(copy_stream)
+                    loss_host[b].copy_(lv, non_blocking=True)
+                    loss_ev[b].record(copy_stream)
+                if marks is not None:
+                    m_ = torch.cuda.Event(enable_timing=True)
+                    m_.record(cur)
+                    marks.append(m_)
                 if i >= 1:                                     # read the previous step's loss on the host
                     loss_ev[1 - b].synchronize()
                     losses.append(float(loss_host[1 - b][0]))
@@ -605,13 +617,17 @@ def main():
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        e2e_loop(K)
+        e2e_marks = [a]
+        e2e_loop(K, e2e_marks)
         if consensus:
             consensus()
         b_.record()
         barrier()
+        e2e_steps = [e2e_marks[i].elapsed_time(e2e_marks[i + 1]) for i in range(len(e2e_marks) - 1)]
         e2e = {"value": nranks * K / (allmax(a.elapsed_time(b_)) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4}
+               "d2h_bytes_per_step": 4,
+               "step_ms": {"first": round(e2e_steps[0], 3), "median": round(sorted(e2e_steps)[len(e2e_steps) // 2], 3),
+                           "max": round(max(e2e_steps), 3), "tail_ms": round(e2e_marks[-1].elapsed_time(b_), 3)}}
 
     # ---- roofline of the dominant kernel (blend backward), timed live with CUDA events ---------------------------
     roofline, stats = None, {}
