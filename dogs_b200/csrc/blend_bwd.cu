@@ -249,8 +249,12 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         if (!(mk & (1u << k))) continue;                    // warp-uniform: the splat cannot reach this 8x4 block
         // power, expf and the alpha threshold are the forward's own expressions, so the contribution
         // decisions and T are those of the forward pass bit for bit.  (A fast ex2.approx exp was
-        // measured: 10 % faster, but the 1e-6 relative change of G decorrelates ill-conditioned conic
-        // gradients from the reference's by up to 5e-4 of the tensor max, outside the 1e-4 parity bar.)
+        // measured again with the FP64 chain rule in place: 1.069 -> 0.991 ms at C3 and the errors against
+        // the FP64 truth stay at 1e-5 — except where the approximate alpha falls on the other side of the
+        // 1/255 threshold than the forward's: the pixel's S then disagrees with the forward's colour and a
+        // handful of elements (3 at C2) leave the 1e-4 bar.  Re-evaluating expf under a warp vote when a
+        // lane is within the approximation error of the threshold restores the errors exactly, but the
+        // vote + compare per (block, entry) and 3 more registers cost more than the exp saves: 1.113 ms.)
         const float dy = b.y - (pyf0 + 4.f * k);
         const float power = -0.5f * (con_o.x * dx * dx + con_o.z * dy * dy) - con_o.y * dx * dy;
         const float G = exp(power);
