@@ -263,10 +263,26 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_cap, int shift, 
   h[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * SORT_CHUNK;
+  // every load of the chunk is in flight before the first count (ncu of the first version: 16 registers, one
+  // load per thread at a time, 49 stall cycles per instruction on the scoreboard, 1.4 TB/s); a full chunk
+  // comes as two 16-byte loads per thread — the order of the keys does not matter to a histogram
+  if (base + SORT_CHUNK <= n) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
+    const uint4 a = k4[threadIdx.x], b = k4[SORT_THREADS + threadIdx.x];
+    atomicAdd(&h[(a.x >> shift) & mask], 1u); atomicAdd(&h[(a.y >> shift) & mask], 1u);
+    atomicAdd(&h[(a.z >> shift) & mask], 1u); atomicAdd(&h[(a.w >> shift) & mask], 1u);
+    atomicAdd(&h[(b.x >> shift) & mask], 1u); atomicAdd(&h[(b.y >> shift) & mask], 1u);
+    atomicAdd(&h[(b.z >> shift) & mask], 1u); atomicAdd(&h[(b.w >> shift) & mask], 1u);
+  } else {
+    uint32_t k[SORT_ITEMS];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
-    uint32_t idx = base + i * SORT_THREADS + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
+    for (int i = 0; i < SORT_ITEMS; i++) {
+      const uint32_t idx = base + i * SORT_THREADS + threadIdx.x;
+      k[i] = idx < n ? keys[idx] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++)
+      if (base + i * SORT_THREADS + threadIdx.x < n) atomicAdd(&h[(k[i] >> shift) & mask], 1u);
   }
   __syncthreads();
   hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
