@@ -307,6 +307,7 @@ int sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_
                    const SortCtl* ctl = nullptr);
 size_t scan_scratch_bytes(size_t n);
 // out[i] = sum_{j<i} in[idx ? idx[j] : j]; total (may be null) receives the grand total.
+int launch_block_base_scan(uint32_t* sums, uint32_t nb, uint32_t* total_out, bool debug, cudaStream_t s);
 int exclusive_scan_u32(const uint32_t* in, const uint32_t* idx, uint32_t* out, uint32_t* total,
                        size_t n, char* scratch, bool debug, cudaStream_t s);
 

@@ -620,6 +620,12 @@ scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ 
   }
 }
 
+// In-place exclusive scan of `nb` block sums by one CTA (the row scan above on a single row); total to *total_out.
+int launch_block_base_scan(uint32_t* sums, uint32_t nb, uint32_t* total_out, bool debug, cudaStream_t s) {
+  launch_pdl(radix_rowscan_kernel, dim3(1), dim3(ROWSCAN_THREADS), 0, s, sums, nb, total_out);
+  return check_launch("block_base_scan", debug, s);
+}
+
 size_t scan_scratch_bytes(size_t n) {
   return align_up(((n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1) * sizeof(uint32_t));
 }

@@ -308,18 +308,35 @@ depth_keys_kernel(int P, const SplatRecord* __restrict__ rec, const uint32_t* __
   depth_key[i] = tiles[i] ? __float_as_uint(rec[i].c.z) : 0xffffffffu;
 }
 
-// emit_rec -> depth order (one 16-byte gather per Gaussian); .y becomes the Gaussian id.
+// emit_rec -> depth order (one 16-byte gather per Gaussian); .y becomes the Gaussian id.  The CTA also leaves the sum
+// of its 256 instance counts in block_sum[blockIdx.x]: scanned by one CTA (radix_rowscan_kernel) these are the
+// bases from which emit_instances_kernel derives every offset itself, so no per-Gaussian offset array is written
+// or read (the three-kernel scan over P counts this replaces: 0.031 ms at 3 M Gaussians).
 __global__ void __launch_bounds__(256)
 gather_emit_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* __restrict__ emit_rec,
-                   uint4* __restrict__ sorted_emit, uint32_t* __restrict__ sorted_cnt) {
+                   uint4* __restrict__ sorted_emit, uint32_t* __restrict__ sorted_cnt, uint32_t* __restrict__ block_sum) {
   pdl_wait();
   pdl_trigger();
+  __shared__ uint32_t wsum[8];
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P) return;
-  const uint32_t id = sorted_idx[j];
-  const uint4 e = emit_rec[id];
-  sorted_cnt[j] = e.y;
-  sorted_emit[j] = make_uint4(e.x, id, e.z, e.w);
+  uint32_t c = 0;
+  if (j < P) {
+    const uint32_t id = sorted_idx[j];
+    const uint4 e = emit_rec[id];
+    c = e.y;
+    sorted_cnt[j] = c;
+    sorted_emit[j] = make_uint4(e.x, id, e.z, e.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += wsum[w];
+    block_sum[blockIdx.x] = t;
+  }
 }
 
 // Small models: the gather and the exclusive scan of the instance counts in depth order (duplicateWithKeys'
@@ -439,7 +456,8 @@ __device__ __forceinline__ int kth_set_bit64(uint32_t lo, uint32_t hi, int k) {
 // Gaussians whose rect exceeds 64 tiles have no mask; the warp re-runs the test for them afterwards.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32_t* __restrict__ sorted_cnt,
-                      const uint32_t* __restrict__ offsets, const SplatRecord* __restrict__ rec,
+                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ block_base,
+                      const SplatRecord* __restrict__ rec,
                       const int* __restrict__ radii, uint32_t* __restrict__ tile_keys,
                       uint32_t* __restrict__ vals, uint32_t gx, uint32_t gy, uint32_t capacity) {
   pdl_wait();
@@ -450,8 +468,27 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
   const uint32_t cnt = i < P ? sorted_cnt[i] : 0u;
   uint4 e = make_uint4(0u, 0u, 0u, 0u);
   if (cnt) e = sorted_emit[i];
-  // offsets[] is the exclusive scan of sorted_cnt: non-decreasing, equal across zero-count entries
-  const uint32_t off = i < P ? offsets[i] : 0xffffffffu;
+  // off = exclusive scan of sorted_cnt: non-decreasing, equal across zero-count entries.  Large models: the CTA's
+  // base (scanned block sums of gather_emit_kernel) + a scan over the CTA's own 256 counts; small models: the
+  // offsets the chained gather + scan kernel wrote.
+  uint32_t off;
+  if (block_base) {
+    __shared__ uint32_t wsum[8];
+    uint32_t x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(full, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t woff = block_base[blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < (int)(threadIdx.x >> 5)) woff += wsum[w];
+    off = i < P ? woff + x - cnt : 0xffffffffu;
+  } else {
+    off = i < P ? offsets[i] : 0xffffffffu;
+  }
   const uint32_t begin = __shfl_sync(full, off, 0);
   uint32_t end = off + cnt;                       // of the last in-range lane
   {
@@ -713,10 +750,10 @@ int launch_gather_scan(const DgrParams& prm, const GeomState& g, const uint32_t*
   if ((size_t)prm.P > GS_CHAINED_MAX) {
     // one 16-byte gather per Gaussian brings everything the emit stage needs into depth order; the scan and
     // the emit kernel then stream sequentially
+    // (g.offsets holds the scanned sums of the emit kernel's 256-Gaussian blocks here, not per-Gaussian offsets)
     launch_pdl(gather_emit_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, sorted_idx,
-               (const uint4*)g.emit_rec, g.sorted_emit, g.sorted_cnt);
-    if (int e = check_launch("gather_emit", prm.debug != 0, s)) return e;
-    return exclusive_scan_u32(g.sorted_cnt, nullptr, g.offsets, total_out, prm.P, scratch, prm.debug != 0, s);
+               (const uint4*)g.emit_rec, g.sorted_emit, g.sorted_cnt, g.offsets);
+    return launch_block_base_scan(g.offsets, (uint32_t)((prm.P + 255) / 256), total_out, prm.debug != 0, s);
   }
   const uint32_t nchunks = (prm.P + GS_CHUNK - 1) / GS_CHUNK;
   uint32_t* status = reinterpret_cast<uint32_t*>(scratch);
@@ -730,8 +767,9 @@ int launch_emit(const DgrParams& prm, const GeomState& g, const int32_t* radii, 
                 uint32_t* vals, uint32_t capacity, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   launch_pdl(emit_instances_kernel, dim3((prm.P + 255) / 256), dim3(256), 0, s, (int)prm.P, (const uint4*)g.sorted_emit,
-             (const uint32_t*)g.sorted_cnt, (const uint32_t*)g.offsets, (const SplatRecord*)g.rec, (const int*)radii, tile_keys,
-             vals, gx, gy, capacity);
+             (const uint32_t*)g.sorted_cnt, (const uint32_t*)g.offsets,
+             (size_t)prm.P > GS_CHAINED_MAX ? (const uint32_t*)g.offsets : (const uint32_t*)nullptr,
+             (const SplatRecord*)g.rec, (const int*)radii, tile_keys, vals, gx, gy, capacity);
   return check_launch("emit_instances", prm.debug != 0, s);
 }
 
