@@ -427,6 +427,11 @@ gather_scan_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* 
   }
 }
 
+__device__ __forceinline__ float emit_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // Position of the (k+1)-th set bit of a 64-bit mask (k < popcount).
 __device__ __forceinline__ int kth_set_bit64(uint32_t lo, uint32_t hi, int k) {
   const int nlo = __popc(lo);
@@ -511,7 +516,10 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
     if (t < end && t < capacity && g_rw) {
       const int bit = kth_set_bit64(g_lo, g_hi, (int)(t - g_off));
       const uint32_t x0 = g_x & 2047u, y0 = (g_x >> 11) & 2047u;
-      const uint32_t ty = (uint32_t)bit / g_rw, tx = (uint32_t)bit - ty * g_rw;
+      // bit < 64 and rect width <= 64: (bit + 0.5) / width stays 1/128 away from every integer, far beyond the
+      // error of the approximate reciprocal, so the truncation is the exact quotient (the integer division was
+      // ~20 instructions of the ~100 per 32 instances)
+      const uint32_t ty = (uint32_t)(((float)bit + 0.5f) * emit_rcp((float)g_rw)), tx = (uint32_t)bit - ty * g_rw;
       tile_keys[t] = (y0 + ty) * gx + x0 + tx;
       vals[t] = g_id;
     }
