@@ -87,7 +87,11 @@ __device__ __forceinline__ V3 color_from_sh(int deg, V3 pos, V3 campos, V3 dc, c
   return {fmaxf(result.x, 0.0f), fmaxf(result.y, 0.0f), fmaxf(result.z, 0.0f)};
 }
 
-constexpr int COOP_RECT_TILES = 16;   // rects with more tiles than this are walked by the whole warp
+__device__ __forceinline__ float emit_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // One thread per Gaussian.  The CTA's slice of the SH tensor (the bulk of the input bytes:
 // 180 of 236 B per Gaussian) is contiguous, so it is staged into shared memory with coalesced
@@ -107,7 +111,8 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       uint8_t* __restrict__ clamped_out, uint32_t* __restrict__ tiles,
                       uint32_t* __restrict__ depth_key, uint4* __restrict__ emit_rec,
                       uint32_t* __restrict__ ctl,
-                      uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing, bool raw_inputs) {
+                      uint32_t gx, uint32_t gy, bool prefiltered, bool antialiasing, bool raw_inputs,
+                      uint32_t walk_off) {
   extern __shared__ __align__(128) float4 sh_stage4[];
   float* sh_stage = reinterpret_cast<float*>(sh_stage4);
   __shared__ __align__(8) uint64_t sh_bar;
@@ -140,11 +145,12 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   uint32_t ntiles = 0, dkey = 0xffffffffu;
   unsigned long long mask = 0ull;
   uint32_t rect_word = 0;
-  // set by lanes whose rect has more than COOP_RECT_TILES tiles: the warp walks those rects together
-  float4 big_co = {0.f, 0.f, 0.f, 0.f};
-  float2 big_xy = {0.f, 0.f};
-  float big_thr = 0.f;
-  int big_x0 = 0, big_y0 = 0, big_w = 0, big_n = 0;
+  // the rect of this lane's Gaussian, walked by the whole warp below (w_n = 0: culled, nothing to walk)
+  float4 w_co = {0.f, 0.f, 0.f, 0.f};
+  float2 w_xy = {0.f, 0.f};
+  float w_thr = 0.f;
+  int w_x0 = 0, w_y0 = 0, w_w = 0;
+  uint32_t w_n = 0;
   do {
     if (idx >= P) break;
     float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
@@ -222,56 +228,76 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     const int rw = rect_max.x - rect_min.x;
     const bool small = rw * (int)(rect_max.y - rect_min.y) <= 64 && rect_min.x < 2048u && rect_min.y < 2048u;
     rect_word = small ? (rect_min.x | (rect_min.y << 11) | ((uint32_t)rw << 22)) : 0u;   // mask fits 64 bits
-    const int ntot = rw * (int)(rect_max.y - rect_min.y);
-    if (ntot > COOP_RECT_TILES) {
-      big_co = co; big_xy = point_image; big_thr = thr;
-      big_x0 = rect_min.x; big_y0 = rect_min.y; big_w = rw; big_n = ntot;
-    } else {
-      const float2 rcps = tile_rcps(co);
-      for (int y = rect_min.y; y < (int)rect_max.y; y++)
-        for (int x = rect_min.x; x < (int)rect_max.x; x++)
-          if (tile_reachable(co, point_image, x, y, thr, rcps)) {
-            ntiles++;
-            mask |= 1ull << ((y - (int)rect_min.y) * rw + (x - (int)rect_min.x));
-          }
-    }
+    w_co = co; w_xy = point_image; w_thr = thr;
+    w_x0 = rect_min.x; w_y0 = rect_min.y; w_w = rw; w_n = (uint32_t)(rw * (int)(rect_max.y - rect_min.y));
     dkey = __float_as_uint(depth);
   } while (0);
-  // Large rects (a few per cent of the Gaussians at C3, the largest ~1000 tiles) are walked by
-  // the whole warp, 32 tiles per step: one thread looping over such a rect alone took longer than the
-  // rest of the grid together (ncu: SMs idle behind a handful of 100-us threads).
+  // Reachability walk over the rects (rasterizer_impl.cu:151-177), by the whole warp over the FLATTENED list of the
+  // (Gaussian, tile) pairs of its 32 Gaussians, 32 pairs per step.  (Second version.  In the first one every thread
+  // walked its own rect, and only rects of more than 16 tiles — the largest ~1000 tiles — were handed to the warp:
+  // the walk was half of this kernel's instructions at 12 of 32 lanes active, because rect sizes within a warp
+  // differ by an order of magnitude.)  A lane finds the owner of its pair by binary search over the lanes'
+  // offsets, reads the owner's parameters from shared memory, tests one tile; the owners collect their bits of
+  // the step's ballot.  The parameter slots alias the warp's own rows of the SH slice, which its lanes have
+  // finished reading (walk_off = 0xffffffff), or lie behind the slice (small SH degrees / precomputed colours).
   {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned big = __ballot_sync(full, big_n > 0);
-    while (big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      const float4 co = {__shfl_sync(full, big_co.x, src), __shfl_sync(full, big_co.y, src),
-                         __shfl_sync(full, big_co.z, src), __shfl_sync(full, big_co.w, src)};
-      const float2 xy = {__shfl_sync(full, big_xy.x, src), __shfl_sync(full, big_xy.y, src)};
-      const float thr = __shfl_sync(full, big_thr, src);
-      const int x0 = __shfl_sync(full, big_x0, src), y0 = __shfl_sync(full, big_y0, src);
-      const int w = __shfl_sync(full, big_w, src), n = __shfl_sync(full, big_n, src);
-      uint32_t cnt = 0, mlo = 0, mhi = 0;
-      const float2 rcps = tile_rcps(co);
-      for (int base = 0; base < n; base += 32) {
-        const int t = base + lane;
-        bool r = false;
-        if (t < n) {
-          const int ty = t / w, tx = t - ty * w;
-          r = tile_reachable(co, xy, x0 + tx, y0 + ty, thr, rcps);
-        }
-        const unsigned b = __ballot_sync(full, r);
-        cnt += __popc(b);
-        if (base == 0) mlo = b;
-        if (base == 32) mhi = b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* slot = walk_off == 0xffffffffu
+                       ? reinterpret_cast<float4*>(reinterpret_cast<char*>(sh_stage) + (size_t)warp * 32 * 3 * M * sizeof(float))
+                       : reinterpret_cast<float4*>(reinterpret_cast<char*>(sh_stage) + walk_off) + warp * 32 * 3;
+    uint32_t incl = w_n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const uint32_t woff = incl - w_n, total = __shfl_sync(full, incl, 31);
+    __syncwarp();                      // every lane of the warp is done with its SH row
+    if (w_n) {
+      const float2 rc = tile_rcps(w_co);
+      slot[3 * lane] = w_co;
+      slot[3 * lane + 1] = make_float4(w_xy.x, w_xy.y, w_thr, rc.x);
+      slot[3 * lane + 2] = make_float4(rc.y, __int_as_float(w_x0), __int_as_float(w_y0), __int_as_float(w_w));
+    }
+    __syncwarp();
+    uint32_t cnt = 0, mlo = 0, mhi = 0;
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t t = base + lane;
+      int g = 0;                       // largest lane with woff <= t: the owner of pair t
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const uint32_t o = __shfl_sync(full, woff, g + step);
+        if (o <= t) g += step;
       }
-      if (lane == src) {
-        ntiles = cnt;
-        mask = ((unsigned long long)mhi << 32) | mlo;   // meaningful only when the rect has <= 64 tiles
+      const uint32_t k = t - __shfl_sync(full, woff, g);
+      bool r = false;
+      if (t < total) {
+        const float4 a = slot[3 * g], b = slot[3 * g + 1], c = slot[3 * g + 2];
+        const int w = __float_as_int(c.w);
+        // k / w: (k + 0.5) / w stays 1/(2w) away from every integer, so for these ranges the truncated product
+        // with an approximate reciprocal is the exact quotient; huge rects take the integer division
+        const int ty = (w <= 128 && k < 16384u) ? (int)(((float)k + 0.5f) * emit_rcp((float)w)) : (int)(k / (uint32_t)w);
+        const int tx = (int)k - ty * w;
+        r = tile_reachable(a, make_float2(b.x, b.y), __float_as_int(c.y) + tx, __float_as_int(c.z) + ty, b.z,
+                           make_float2(b.w, c.x));
+      }
+      const unsigned bal = __ballot_sync(full, r);
+      // this lane's span [sa, sb) of the step's 32 pairs
+      const int sa = max((int)woff - (int)base, 0), sb = min((int)(woff + w_n) - (int)base, 32);
+      if (sb > sa) {
+        const uint32_t seg = (bal >> sa) & (sb - sa == 32 ? 0xffffffffu : (1u << (sb - sa)) - 1u);
+        cnt += __popc(seg);
+        const int j0 = (int)base + sa - (int)woff;      // rect-local index of the span's first pair
+        if (j0 < 64) {                                   // (the mask is only used for rects of <= 64 tiles)
+          const unsigned long long m = (unsigned long long)seg << j0;
+          mlo |= (uint32_t)m;
+          mhi |= (uint32_t)(m >> 32);
+        }
       }
     }
+    ntiles = cnt;
+    mask = ((unsigned long long)mhi << 32) | mlo;
   }
   // range of the depth keys that take part in the sort (ctl[0] = min, ctl[1] = max): one reduction per CTA
   {
@@ -427,11 +453,6 @@ gather_scan_kernel(int P, const uint32_t* __restrict__ sorted_idx, const uint4* 
   }
 }
 
-__device__ __forceinline__ float emit_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 // Position of the (k+1)-th set bit of a 64-bit mask (k < popcount).
 __device__ __forceinline__ int kth_set_bit64(uint32_t lo, uint32_t hi, int k) {
   const int nlo = __popc(lo);
@@ -728,6 +749,13 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   const bool use_sh = colors_precomp == nullptr && prm.D > 0 && prm.M > 0;
   size_t smem = use_sh ? (size_t)PRE_THREADS * 3 * prm.M * sizeof(float) + 16 : 0;
+  // parameter slots of the cooperative rect walk: 48 bytes per thread, inside the warp's own SH rows when those
+  // are large enough (3 M floats per thread >= 48 bytes), else behind the slice
+  uint32_t walk_off = 0xffffffffu;
+  if (!use_sh || (size_t)3 * prm.M * sizeof(float) < 48) {
+    walk_off = (uint32_t)((smem + 15) & ~(size_t)15);
+    smem = walk_off + (size_t)PRE_THREADS * 48;
+  }
   static bool attr_set[64] = {};
   allow_big_smem(preprocess_fwd_kernel, attr_set);
   if (smem > 96 * 1024) {
@@ -738,7 +766,7 @@ int launch_preprocess_fwd(const DgrParams& prm, const float* means3D, const floa
       prm.P, prm.D, prm.M, means3D, scales, prm.scale_modifier, rotations, opacities, dc, sh,
       cov3D_precomp, colors_precomp, prm.viewmatrix, prm.projmatrix, prm.campos, prm.W, prm.H,
       prm.tanfovx, prm.tanfovy, focal_x, focal_y, radii, g.rec, g.clamped, g.tiles, g.depth_key,
-      g.emit_rec, g.ctl, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0, prm.raw_inputs != 0);
+      g.emit_rec, g.ctl, gx, gy, prm.prefiltered != 0, prm.antialiasing != 0, prm.raw_inputs != 0, walk_off);
   return check_launch("preprocess_fwd", prm.debug != 0, s);
 }
 
