@@ -126,7 +126,8 @@ def end_deferred_checks():
 
 
 def _params(rs, P, M, device, backward=False):
-    f = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+    f = lambda t: t if (t.device == device and t.dtype is torch.float32 and t.is_contiguous()) \
+        else t.to(device=device, dtype=torch.float32).contiguous()
     keep = (f(rs.bg), f(rs.viewmatrix), f(rs.projmatrix), f(rs.campos))
     prm = L.DgrParams(
         P=P, D=int(rs.sh_degree), M=M, W=int(rs.image_width), H=int(rs.image_height),
@@ -226,7 +227,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         invdepth = torch.empty((1, H, W), dtype=torch.float32, device=device)
         radii = torch.empty((P,), dtype=torch.int32, device=device)
-        geom, binning, image, scratch = (L.Allocator(device) for _ in range(4))
+        geom, binning, image, scratch = L.take_allocators(device, 4)
         num_rendered = 0
         if P != 0:
             prm, keep = _params(rs, P, M, device)
@@ -244,7 +245,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 prm.instance_capacity = cap
                 prm.deferred_check = _RECORDER.take(device.index or 0, cap, prm.depth_key_bits)
             info = L.DgrForwardInfo()
-            with torch.cuda.device(device):
+            with L.on_device(device):
                 args = (C.byref(prm), L.ptr(means3D), L.ptr(dc), L.ptr(sh), L.ptr(colors_precomp),
                         L.ptr(opacities), L.ptr(scales), L.ptr(rotations), L.ptr(cov3Ds_precomp),
                         color.data_ptr(), invdepth.data_ptr(), radii.data_ptr(),
@@ -271,11 +272,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.M = M
-        empty = torch.empty(0, dtype=torch.uint8, device=device)
+        g_buf, b_buf, i_buf = geom.last, binning.last, image.last
+        if g_buf is None or b_buf is None or i_buf is None:
+            empty = torch.empty(0, dtype=torch.uint8, device=device)
+            g_buf = empty if g_buf is None else g_buf
+            b_buf = empty if b_buf is None else b_buf
+            i_buf = empty if i_buf is None else i_buf
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, dc,
-                              sh, opacities, geom.last if geom.last is not None else empty,
-                              binning.last if binning.last is not None else empty,
-                              image.last if image.last is not None else empty)
+                              sh, opacities, g_buf, b_buf, i_buf)
+        L.give_back((geom, binning, image, scratch))     # with empty buffer lists: ctx owns the state buffers now
         ctx.mark_non_differentiable(radii)
         # an output the loss does not use arrives as None in backward (no zero image is materialised, and
         # the blend backward compiles its depth terms out)
@@ -306,8 +311,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_out_color = grad_out_color.contiguous()
             if grad_out_depth is not None:
                 grad_out_depth = grad_out_depth.contiguous()
-            scratch = L.Allocator(device)
-            with torch.cuda.device(device):
+            scratch, = L.take_allocators(device, 1)
+            with L.on_device(device):
                 args = (C.byref(prm), ctx.num_rendered, L.ptr(means3D), L.ptr(dc), L.ptr(sh),
                         L.ptr(colors_precomp), L.ptr(opacities), L.ptr(scales), L.ptr(rotations),
                         L.ptr(cov3Ds_precomp), radii.data_ptr(), geomBuffer.data_ptr(),
@@ -328,6 +333,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                         raise ex
                 else:
                     L.check(L.lib().dgr_backward(*args))
+            L.give_back((scratch,))      # stream-ordered: the accumulator may return to the caching allocator now
             del keep
         # depth_threshold scaling of grad_means2D (reference __init__.py:171-185) is fused into
         # the preprocess-backward kernel.

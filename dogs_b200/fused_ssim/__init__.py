@@ -92,11 +92,28 @@ _loss_ws = {}   # (device, stream) -> 32-byte workspace, zeroed once; the kernel
 
 
 def _workspace(device):
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    key = (device, L.stream_ptr(device))
     ws = _loss_ws.get(key)
     if ws is None:
         ws = _loss_ws[key] = torch.zeros(4, dtype=torch.float64, device=device)
     return ws
+
+
+_weights_memo = {}
+
+
+def _loss_weights(lambda_dssim, numel):
+    """The per-pixel weights autograd would produce in float32: (-lambda) / N and (1 - lambda) / N (memoised: two
+    CPU tensor divisions per step otherwise)."""
+    key = (lambda_dssim, numel)
+    w = _weights_memo.get(key)
+    if w is None:
+        n = torch.tensor(float(numel), dtype=torch.float32)
+        lam = torch.tensor(lambda_dssim, dtype=torch.float32)
+        if len(_weights_memo) > 64:
+            _weights_memo.clear()
+        w = _weights_memo[key] = (float(-lam / n), float((1.0 - lam) / n))
+    return w
 
 
 class _L1SSIMLoss(torch.autograd.Function):
@@ -109,7 +126,7 @@ class _L1SSIMLoss(torch.autograd.Function):
         train = ctx.needs_input_grad[0]
         maps = [torch.empty_like(img1) for _ in range(3)] if train else [None] * 3
         loss = torch.empty((), dtype=torch.float32, device=img1.device)
-        with torch.cuda.device(img1.device):
+        with L.on_device(img1.device):
             L.check(L.lib().fssim_l1_loss_forward(B, CH, H, W, _C1, _C2, float(lambda_dssim), img1.data_ptr(),
                                                   img2.data_ptr(), L.ptr(maps[0]), L.ptr(maps[1]), L.ptr(maps[2]),
                                                   _workspace(img1.device).data_ptr(), loss.data_ptr(),
@@ -123,14 +140,10 @@ class _L1SSIMLoss(torch.autograd.Function):
     def backward(ctx, grad_loss):
         img1, img2, *maps = ctx.saved_tensors
         B, CH, H, W = img1.shape
-        # the per-pixel weights autograd would produce in float32: (-lambda) / N and (1 - lambda) / N
-        n = torch.tensor(float(img1.numel()), dtype=torch.float32)
-        lam = torch.tensor(ctx.lambda_dssim, dtype=torch.float32)
-        w_ssim = float(-lam / n)
-        w_l1 = float((1.0 - lam) / n)
+        w_ssim, w_l1 = _loss_weights(ctx.lambda_dssim, img1.numel())
         grad_loss = L.require_cuda(grad_loss, "grad_loss")
         grad = torch.empty_like(img1)
-        with torch.cuda.device(img1.device):
+        with L.on_device(img1.device):
             L.check(L.lib().fssim_l1_loss_backward(B, CH, H, W, w_ssim, w_l1, img1.data_ptr(), img2.data_ptr(),
                                                    maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(),
                                                    grad_loss.data_ptr(), grad.data_ptr(),
