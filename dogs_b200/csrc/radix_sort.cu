@@ -11,7 +11,7 @@
 // a scan of the 256 x nblk count matrix, ranked scatter — and read the keys twice per pass; the
 // chain of ~15 short launches was most of the binning time of small scenes.  Now ONE kernel reads
 // the keys once and produces the digit totals of EVERY pass, and each pass is a single kernel: a
-// CTA ranks its 2048 keys, publishes its 256 digit counts, and obtains the sum over the CTAs
+// CTA ranks its chunk of keys (SORT_CHUNK = 3072), publishes its 256 digit counts, and obtains the sum over the CTAs
 // before it by looking back over their published counts (chained scan with decoupled look-back:
 // status word = 2 flag bits + 30-bit count, "local count" first, "inclusive prefix" once known).
 // CTAs take their chunk number from a ticket counter, so every chunk a CTA waits for is owned by
@@ -25,7 +25,11 @@
 namespace dogs {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 8;
+#ifndef SORT_ITEMS_N
+#define SORT_ITEMS_N 12    // keys per thread (a multiple of 4).  Measured at C3: 8 / 12 / 16 -> depth sort 0.101 / 0.098 / 0.100 ms,
+                          // tile sort 0.183 / 0.173 / 0.185 ms (16: 89 registers, 2 CTAs/SM)
+#endif
+constexpr int SORT_ITEMS = SORT_ITEMS_N;
 constexpr int SORT_CHUNK = SORT_THREADS * SORT_ITEMS;  // keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
@@ -265,14 +269,17 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_cap, int shift, 
   const uint32_t base = blockIdx.x * SORT_CHUNK;
   // every load of the chunk is in flight before the first count (ncu of the first version: 16 registers, one
   // load per thread at a time, 49 stall cycles per instruction on the scoreboard, 1.4 TB/s); a full chunk
-  // comes as two 16-byte loads per thread — the order of the keys does not matter to a histogram
+  // comes as 16-byte loads, two per thread — the order of the keys does not matter to a histogram
   if (base + SORT_CHUNK <= n) {
     const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
-    const uint4 a = k4[threadIdx.x], b = k4[SORT_THREADS + threadIdx.x];
-    atomicAdd(&h[(a.x >> shift) & mask], 1u); atomicAdd(&h[(a.y >> shift) & mask], 1u);
-    atomicAdd(&h[(a.z >> shift) & mask], 1u); atomicAdd(&h[(a.w >> shift) & mask], 1u);
-    atomicAdd(&h[(b.x >> shift) & mask], 1u); atomicAdd(&h[(b.y >> shift) & mask], 1u);
-    atomicAdd(&h[(b.z >> shift) & mask], 1u); atomicAdd(&h[(b.w >> shift) & mask], 1u);
+    uint4 v[SORT_ITEMS / 4];
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS / 4; q++) v[q] = k4[q * SORT_THREADS + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < SORT_ITEMS / 4; q++) {
+      atomicAdd(&h[(v[q].x >> shift) & mask], 1u); atomicAdd(&h[(v[q].y >> shift) & mask], 1u);
+      atomicAdd(&h[(v[q].z >> shift) & mask], 1u); atomicAdd(&h[(v[q].w >> shift) & mask], 1u);
+    }
   } else {
     uint32_t k[SORT_ITEMS];
 #pragma unroll

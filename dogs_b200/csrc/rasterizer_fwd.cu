@@ -8,7 +8,10 @@
 
 namespace dogs {
 
-constexpr int PRE_THREADS = 128;
+#ifndef PRE_THREADS_N
+#define PRE_THREADS_N 128
+#endif
+constexpr int PRE_THREADS = PRE_THREADS_N;
 
 // ---- forward.cu:119-153 ----------------------------------------------------------
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot,
@@ -587,26 +590,29 @@ emit_instances_kernel(int P, const uint4* __restrict__ sorted_emit, const uint32
 }
 
 // identifyTileRanges (rasterizer_impl.cu:195-220) on 32-bit tile keys; no pad entries exist.
-// Four consecutive keys per thread (one 16-byte load + the predecessor).
+// Eight consecutive keys per thread (two 16-byte loads + the predecessor, all requested before the first compare).
+constexpr int TR_KEYS = 8;
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(uint32_t L_cap, const uint32_t* __restrict__ L_dev, const uint32_t* __restrict__ tile_keys,
                    uint2* __restrict__ ranges, uint32_t T) {
   pdl_wait();
   pdl_trigger();
   const uint32_t L = L_dev ? min(*L_dev, L_cap) : L_cap;
-  const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * (uint32_t)TR_KEYS;
   if (i0 >= L) return;
-  const uint32_t n = min(4u, L - i0);
-  uint32_t k[4] = {0u, 0u, 0u, 0u};
-  if (n == 4) {
-    const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + i0);
-    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+  const uint32_t n = min((uint32_t)TR_KEYS, L - i0);
+  uint32_t k[TR_KEYS];
+#pragma unroll
+  for (int q = 0; q < TR_KEYS; q++) k[q] = 0u;
+  uint32_t prev = i0 ? tile_keys[i0 - 1] : 0u;
+  if (n == TR_KEYS) {
+    const uint4 v = *reinterpret_cast<const uint4*>(tile_keys + i0), w = *reinterpret_cast<const uint4*>(tile_keys + i0 + 4);
+    k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w; k[4] = w.x; k[5] = w.y; k[6] = w.z; k[7] = w.w;
   } else {
     for (uint32_t q = 0; q < n; q++) k[q] = tile_keys[i0 + q];
   }
-  uint32_t prev = i0 ? tile_keys[i0 - 1] : 0u;
 #pragma unroll
-  for (uint32_t q = 0; q < 4; q++) {
+  for (uint32_t q = 0; q < (uint32_t)TR_KEYS; q++) {
     if (q >= n) break;
     const uint32_t idx = i0 + q, cur = k[q];
     if (cur < T) {        // (a slot the emit stage left unwritten would carry garbage: never index with it)
@@ -813,7 +819,7 @@ int launch_tile_ranges(const DgrParams& prm, uint32_t R, const uint32_t* R_dev, 
                        uint2* ranges, cudaStream_t s) {
   const uint32_t gx = (prm.W + TILE_X - 1) / TILE_X, gy = (prm.H + TILE_Y - 1) / TILE_Y;
   cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), s);
-  if (R > 0) launch_pdl(tile_ranges_kernel, dim3((R + 1023) / 1024), dim3(256), 0, s, R, R_dev, tile_keys, ranges, gx * gy);
+  if (R > 0) launch_pdl(tile_ranges_kernel, dim3((R + 256 * TR_KEYS - 1) / (256 * TR_KEYS)), dim3(256), 0, s, R, R_dev, tile_keys, ranges, gx * gy);
   return check_launch("tile_ranges", prm.debug != 0, s);
 }
 
