@@ -286,6 +286,39 @@ def test_edge_cases():
              shs=sc["sh"].cpu(), dc=sc["dc"].cpu(), scales=sc["scales"].cpu(), rotations=sc["rotations"].cpu())
 
 
+@pytest.mark.parametrize("degree", [1, 2])
+def test_low_sh_degree_vs_reference(degree):
+    """SH degrees 1 and 2 (M = 3 / 8 rest coefficients): the parameter slots of the cooperative rect walk lie
+    behind the staged SH slice (M = 3: a thread's SH row is shorter than a slot) or inside the warp's own rows
+    (M = 8); instance lists, contributor counts and image against the reference build."""
+    dgr = _need_ref()
+    spec = scenes.SPECS["tiny"]._replace(W=400, H=304)
+    sc = scenes.make_scene(spec, 31, DEV, P=3000)
+    g = torch.Generator(device="cpu").manual_seed(32)
+    mult = torch.exp(torch.rand(3000, 1, generator=g) * 4.0).to(DEV)
+    M = (degree + 1) ** 2 - 1
+    sc = dict(sc, scales=(sc["scales"] * mult).contiguous(), sh=sc["sh"][:, :M].contiguous(), sh_degree=degree)
+    r = U.ref_forward_raw(dgr, sc)
+    o = U.ours_forward_raw(sc)
+    H, W = sc["H"], sc["W"]
+    ri = U.parse_ref_image(r["img"], H * W)
+    assert torch.equal(r["radii"], o["radii"])
+    rb = U.parse_ref_binning(r["binning"], r["num_rendered"])
+    valid = ((rb["keys"] >> 32) & 0xFFFFFFFF) != 0xFFFFFFFF
+    keys = (o["tile_keys"].long() << 32) | (U.bits(o["depths"]).long()[o["point_list"].long()] & 0xFFFFFFFF)
+    assert torch.equal(rb["keys"][valid], keys)
+    assert torch.equal(rb["point_list"][valid].long(), o["point_list"].long())
+    assert torch.equal(ri["n_contrib"], o["n_contrib"])
+    assert (r["color"] - o["color"]).abs().max().item() <= IMG_TOL
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ri["max_contrib"][:T] = U.tile_max(ri["n_contrib"], H, W)
+    dLc, dLd = _out_grads(sc)
+    gr = U.ref_backward_raw(dgr, sc, r, dLc, dLd)
+    go = U.ours_backward(sc, dLc, dLd)
+    for k in ("means3D", "dc", "sh", "opacities", "scales", "rotations"):
+        assert U.rel_to_max(go[k], gr[k].reshape(go[k].shape)) <= GRAD_TOL, k
+
+
 def test_ragged_image_and_nonzero_background_vs_reference():
     """Image size not a multiple of the tile, bg != 0 (the reference counts bg twice in dL/dalpha)."""
     dgr = _need_ref()
@@ -314,9 +347,10 @@ def test_ragged_image_and_nonzero_background_vs_reference():
 
 @pytest.mark.parametrize("P", [1, 31, 77, 1000])
 def test_mixed_rect_sizes_vs_reference(P):
-    """Every branch of the rect walk in preprocess / emit: Gaussians whose rect has <= 16 tiles (walked
-    by their own thread), 17-64 tiles (walked by the warp, bit mask recorded) and > 64 tiles up to the
-    whole image (walked by the warp again at emission), in warps that are only partly populated."""
+    """Every branch of the rect walk in preprocess / emit: the warp walks the flattened (Gaussian, tile) pairs of
+    its 32 Gaussians; rects of <= 64 tiles record a bit mask, rects of > 64 tiles up to the whole image are walked
+    again by the warp at emission; rect sizes from 1 to > 500 tiles meet in one warp, in warps that are only
+    partly populated."""
     dgr = _need_ref()
     spec = scenes.SPECS["tiny"]._replace(W=400, H=304)
     sc = scenes.make_scene(spec, 21, DEV, P=P)
