@@ -420,35 +420,47 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     if (admm.zmu_xyz) {
       // Fused ADMM penalty (slave_gaussian_trainer.py:161-202) on the consensus variables that are
       // direct rasterizer inputs: grad += rho_g/numel_g * (x - (z - u)), for EVERY Gaussian of the block.
-      const float r0 = means3D[3 * idx] - admm.zmu_xyz[3 * idx];
-      const float r1 = means3D[3 * idx + 1] - admm.zmu_xyz[3 * idx + 1];
-      const float r2 = means3D[3 * idx + 2] - admm.zmu_xyz[3 * idx + 2];
-      g_mean3D.x += admm.coef_xyz * r0; g_mean3D.y += admm.coef_xyz * r1; g_mean3D.z += admm.coef_xyz * r2;
-      pen_xyz = (double)(r0 * r0 + r1 * r1 + r2 * r2);
-      if (dL_ddc && admm.zmu_dc) {
-        const float q0 = dc[3 * idx] - admm.zmu_dc[3 * idx];
-        const float q1 = dc[3 * idx + 1] - admm.zmu_dc[3 * idx + 1];
-        const float q2 = dc[3 * idx + 2] - admm.zmu_dc[3 * idx + 2];
+      // Every load of the five groups is requested before the first value is used, in ONE basic block (predicated
+      // loads instead of one `if` per group): ncu showed five waits for memory in a row here, one per group —
+      // 16 % of this kernel's stall samples — because loads are not moved across the groups' branches.
+      const bool p_dc = dL_ddc && admm.zmu_dc, p_sc = dL_dscales && admm.zmu_scale;
+      const bool p_rot = dL_drots && admm.zmu_rot, p_op = admm.zmu_opacity != nullptr;
+      const float zx0 = admm.zmu_xyz[3 * idx], zx1 = admm.zmu_xyz[3 * idx + 1], zx2 = admm.zmu_xyz[3 * idx + 2];
+      const float zd0 = p_dc ? admm.zmu_dc[3 * idx] : 0.f, zd1 = p_dc ? admm.zmu_dc[3 * idx + 1] : 0.f,
+                  zd2 = p_dc ? admm.zmu_dc[3 * idx + 2] : 0.f;
+      const float zs0 = p_sc ? admm.zmu_scale[3 * idx] : 0.f, zs1 = p_sc ? admm.zmu_scale[3 * idx + 1] : 0.f,
+                  zs2 = p_sc ? admm.zmu_scale[3 * idx + 2] : 0.f;
+      const float4 zero4 = {0.f, 0.f, 0.f, 0.f};
+      const float4 zr = p_rot ? reinterpret_cast<const float4*>(admm.zmu_rot)[idx] : zero4;
+      const float zo = p_op ? admm.zmu_opacity[idx] : 0.f;
+      const float x0 = means3D[3 * idx], x1 = means3D[3 * idx + 1], x2 = means3D[3 * idx + 2];
+      const float d0 = p_dc ? dc[3 * idx] : 0.f, d1 = p_dc ? dc[3 * idx + 1] : 0.f, d2 = p_dc ? dc[3 * idx + 2] : 0.f;
+      const float s0 = p_sc ? scales[3 * idx] : 0.f, s1 = p_sc ? scales[3 * idx + 1] : 0.f, s2 = p_sc ? scales[3 * idx + 2] : 0.f;
+      const float4 xr = p_rot ? reinterpret_cast<const float4*>(rotations)[idx] : zero4;
+      const float xo = p_op ? opacities[idx] : 0.f;
+      {
+        const float r0 = x0 - zx0, r1 = x1 - zx1, r2 = x2 - zx2;
+        g_mean3D.x += admm.coef_xyz * r0; g_mean3D.y += admm.coef_xyz * r1; g_mean3D.z += admm.coef_xyz * r2;
+        pen_xyz = (double)(r0 * r0 + r1 * r1 + r2 * r2);
+      }
+      if (p_dc) {
+        const float q0 = d0 - zd0, q1 = d1 - zd1, q2 = d2 - zd2;
         g_dc.x += admm.coef_dc * q0; g_dc.y += admm.coef_dc * q1; g_dc.z += admm.coef_dc * q2;
         pen_dc = (double)(q0 * q0 + q1 * q1 + q2 * q2);
       }
       // the remaining groups: the tensors as passed are the consensus variables (raw_inputs)
-      if (dL_dscales && admm.zmu_scale) {
-        const float q0 = scales[3 * idx] - admm.zmu_scale[3 * idx];
-        const float q1 = scales[3 * idx + 1] - admm.zmu_scale[3 * idx + 1];
-        const float q2 = scales[3 * idx + 2] - admm.zmu_scale[3 * idx + 2];
+      if (p_sc) {
+        const float q0 = s0 - zs0, q1 = s1 - zs1, q2 = s2 - zs2;
         g_scale[0] += admm.coef_scale * q0; g_scale[1] += admm.coef_scale * q1; g_scale[2] += admm.coef_scale * q2;
         pen_scale = (double)(q0 * q0 + q1 * q1 + q2 * q2);
       }
-      if (dL_drots && admm.zmu_rot) {
-        const float4 xr = reinterpret_cast<const float4*>(rotations)[idx];
-        const float4 zr = reinterpret_cast<const float4*>(admm.zmu_rot)[idx];
+      if (p_rot) {
         const float q0 = xr.x - zr.x, q1 = xr.y - zr.y, q2 = xr.z - zr.z, q3 = xr.w - zr.w;
         g_rot.x += admm.coef_rot * q0; g_rot.y += admm.coef_rot * q1; g_rot.z += admm.coef_rot * q2; g_rot.w += admm.coef_rot * q3;
         pen_rot = (double)(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
       }
-      if (admm.zmu_opacity) {
-        const float q0 = opacities[idx] - admm.zmu_opacity[idx];
+      if (p_op) {
+        const float q0 = xo - zo;
         g_opacity += admm.coef_opacity * q0;
         pen_op = (double)(q0 * q0);
       }
@@ -485,15 +497,18 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
       const float4* x4 = reinterpret_cast<const float4*>(xs);
       const float4* z4 = reinterpret_cast<const float4*>(zs);
       float acc = 0.f;
-      for (size_t base = 0; base < n4; base += PREB_THREADS * 4) {
-        float4 xv[4], zv[4];
+      // (PEN_BATCH vectors per thread and array in flight: the 11.25 vectors a thread owns of a degree-3 slice take
+      //  two rounds of 6 — with rounds of 4 the third wait for memory was 5 % of the kernel)
+      constexpr int PEN_BATCH = 6;
+      for (size_t base = 0; base < n4; base += PREB_THREADS * PEN_BATCH) {
+        float4 xv[PEN_BATCH], zv[PEN_BATCH];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < PEN_BATCH; k++) {
           const size_t i = base + k * PREB_THREADS + threadIdx.x;
           if (i < n4) { xv[k] = __ldg(x4 + i); zv[k] = __ldg(z4 + i); }
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < PEN_BATCH; k++) {
           const size_t i = base + k * PREB_THREADS + threadIdx.x;
           if (i < n4) {
             float4 g = stage4[i];
@@ -503,7 +518,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
             stage4[i] = g;
           }
         }
-        pen_sh += (double)acc;             // <= 16 squares per step in float, everything above in double
+        pen_sh += (double)acc;             // <= 24 squares per step in float, everything above in double
         acc = 0.f;
       }
       for (size_t i = (n4 << 2) + threadIdx.x; i < nfl; i += PREB_THREADS) {
