@@ -341,28 +341,52 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     float g_scale[3] = {0.f, 0.f, 0.f};
     float4 g_rot = {0.f, 0.f, 0.f, 0.f};
     float g_cov3D[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const bool visible = radii[idx] > 0;
+    // Every per-Gaussian input is requested here, before the first of them is needed.  (ncu, stall samples by
+    // source line: the visibility test, the accumulator / mean / opacity loads, the scale / rotation loads inside
+    // their `if`, and the clamp flags inside the SH branch were four memory round trips in a row — loads are not
+    // moved across the branches that separate them.  The asm statements are volatile so that they stay put.)
+    int rad_in;
+    float4 A0, A1, A2, rot_in = {0.f, 0.f, 0.f, 0.f};
+    float3 mean_in, scale_in = {0.f, 0.f, 0.f};
+    float opac_in;
+    uint32_t clamp_in;
+    {
+      const float4* acc4 = reinterpret_cast<const float4*>(accum + (size_t)idx * ACC_STRIDE);
+      asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(rad_in) : "l"(radii + idx));
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A0.x), "=f"(A0.y), "=f"(A0.z), "=f"(A0.w) : "l"(acc4));
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A1.x), "=f"(A1.y), "=f"(A1.z), "=f"(A1.w) : "l"(acc4 + 1));
+      asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A2.x), "=f"(A2.y), "=f"(A2.z), "=f"(A2.w) : "l"(acc4 + 2));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(mean_in.x) : "l"(means3D + 3 * idx));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(mean_in.y) : "l"(means3D + 3 * idx + 1));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(mean_in.z) : "l"(means3D + 3 * idx + 2));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(opac_in) : "l"(opacities + idx));
+      asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(clamp_in) : "l"(clamped + idx));
+      if (cov3D_precomp == nullptr) {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(scale_in.x) : "l"(scales + 3 * idx));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(scale_in.y) : "l"(scales + 3 * idx + 1));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(scale_in.z) : "l"(scales + 3 * idx + 2));
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(rot_in.x), "=f"(rot_in.y), "=f"(rot_in.z), "=f"(rot_in.w)
+                     : "l"(reinterpret_cast<const float4*>(rotations) + idx));
+      }
+    }
+    const bool visible = rad_in > 0;
     if (!visible) {
       if (sh_path) {
         if (bulk) mbar_wait(&sh_bar, 0);     // the incoming copy must not land on top of the zeros
         for (int i = 0; i < 3 * M; i++) sh_row[i] = 0.f;
       }
     } else {
-      const float4* acc4 = reinterpret_cast<const float4*>(accum + (size_t)idx * ACC_STRIDE);
-      const float4 A0 = acc4[0], A1 = acc4[1], A2 = acc4[2];
       const float2 dL_dmean2D = {A0.x, A0.y};
       float3 dL_dconic = {A0.z, A0.w, A1.x};
       float dL_dopac = A1.y;
       g_color[0] = A1.z; g_color[1] = A1.w; g_color[2] = A2.x;
       const float dL_dinvdepth = A2.y;
 
-      const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-      float3 scale = {0.f, 0.f, 0.f};
-      float4 rot = {0.f, 0.f, 0.f, 0.f}, raw_rot = {0.f, 0.f, 0.f, 0.f};
-      const float opac = raw_inputs ? act_sigmoid(opacities[idx]) : opacities[idx];
+      const float3 mean = mean_in;
+      float3 scale = scale_in;
+      float4 rot = rot_in, raw_rot = {0.f, 0.f, 0.f, 0.f};
+      const float opac = raw_inputs ? act_sigmoid(opac_in) : opac_in;
       if (cov3D_precomp == nullptr) {
-        scale = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-        rot = reinterpret_cast<const float4*>(rotations)[idx];
         if (raw_inputs) { raw_rot = rot; scale = act_exp3(scale); rot = act_normalize(rot); }
       }
       float depth;
@@ -384,12 +408,12 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
         V3 pos = {mean.x, mean.y, mean.z};
         V3 cp = {campos[0], campos[1], campos[2]};
         V3 dLc = {g_color[0], g_color[1], g_color[2]};
-        V3 dm = sh_backward(D, M, pos, cp, clamped[idx], dLc, sh_row, g_dc);
+        V3 dm = sh_backward(D, M, pos, cp, clamp_in, dLc, sh_row, g_dc);
         g_mean3D.x += dm.x; g_mean3D.y += dm.y; g_mean3D.z += dm.z;
       } else if (dL_ddc != nullptr) {
         // degree-0 model without a rest tensor (M == 0): the colour is SH_C0 * dc + 0.5 and only dc gets a gradient
         // (the reference's `if (shs)` branch, backward.cu:445-447, is never taken for it and its dc never trains)
-        const uint32_t cl = clamped[idx];
+        const uint32_t cl = clamp_in;
         g_dc = {(cl & 1u) ? 0.f : SH_C0 * g_color[0], (cl & 2u) ? 0.f : SH_C0 * g_color[1], (cl & 4u) ? 0.f : SH_C0 * g_color[2]};
       }
 
