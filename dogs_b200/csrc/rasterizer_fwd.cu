@@ -157,6 +157,18 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
   do {
     if (idx >= P) break;
     float3 p_orig = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    // The opacity and the dc colour are requested here, with the position, not where they are used (after the
+    // frustum and rect tests): loads are not moved across those branches, and each was a memory round trip of its
+    // own.  (Hoisting the scale / rotation loads as well changes ptxas' FMA contraction in the covariance code —
+    // conics 1-2 ulp off the reference's — so those stay where they are.)
+    float op_in;
+    float3 dc_in = {0.f, 0.f, 0.f};
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(op_in) : "l"(opacities + idx));
+    if (colors_precomp == nullptr) {
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dc_in.x) : "l"(dc + 3 * idx));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dc_in.y) : "l"(dc + 3 * idx + 1));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dc_in.z) : "l"(dc + 3 * idx + 2));
+    }
     // auxiliary.h:150-175 in_frustum
     float4 p_hom = xform4x4(p_orig, proj);
     float p_w = 1.0f / (p_hom.w + 0.0000001f);
@@ -207,7 +219,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     if (colors_precomp == nullptr) {
       V3 pos = {p_orig.x, p_orig.y, p_orig.z};
       V3 cp = {cam_pos[0], cam_pos[1], cam_pos[2]};
-      V3 d0 = {dc[3 * idx], dc[3 * idx + 1], dc[3 * idx + 2]};
+      V3 d0 = {dc_in.x, dc_in.y, dc_in.z};
       if (bulk) mbar_wait(&sh_bar, 0);
       V3 c = color_from_sh(D, pos, cp, d0, sh_stage + (size_t)threadIdx.x * 3 * M, clamped);
       rgb = {c.x, c.y, c.z};
@@ -217,7 +229,7 @@ preprocess_fwd_kernel(int P, int D, int M, const float* __restrict__ means3D,
     clamped_out[idx] = (uint8_t)clamped;
 
     const float depth = p_view.z;
-    const float opacity = (raw_inputs ? act_sigmoid(opacities[idx]) : opacities[idx]) * h_convolution_scaling;
+    const float opacity = (raw_inputs ? act_sigmoid(op_in) : op_in) * h_convolution_scaling;
     radius_out = (int)my_radius;
     const float4 co = {conic.x, conic.y, conic.z, opacity};
     SplatRecord r;
