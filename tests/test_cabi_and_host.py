@@ -162,3 +162,39 @@ def test_oracle_statistics_match_survey_prediction():
     R = int(pre["tiles_touched"].sum())
     assert 0.93 < vis < 0.99
     assert abs(R - 670_000) / 670_000 < 0.10
+
+
+def test_allocator_pool_hands_back_empty_allocators():
+    """The allocation callbacks are reused between calls (dogs_b200/_lib.py): an allocator returns to the pool with an
+    empty buffer list, so the pool never keeps memory alive, and a reused callback serves fresh buffers."""
+    from dogs_b200 import _lib as L
+    dev = torch.device("cpu")
+    L._alloc_pool.pop(dev, None)
+    a, b = L.take_allocators(dev, 2)
+    assert a is not b and a.last is None
+    p1 = a.cb(None, 64)
+    assert p1 == a.last.data_ptr() and a.last.numel() == 64
+    p0 = a.cb(None, 0)                       # zero-byte requests still get a valid pointer
+    assert p0 == a.last.data_ptr() and a.last.numel() == 1 and len(a.buffers) == 2
+    keep = a.buffers[0]
+    L.give_back((a, b))
+    assert a.buffers == [] and keep.numel() == 64          # the caller's reference survives, the pool holds nothing
+    c, d = L.take_allocators(dev, 2)
+    assert {id(c), id(d)} == {id(a), id(b)}                  # reused, not rebuilt
+    c.cb(None, 16)
+    assert c.last.numel() == 16
+    L.give_back((c, d))
+    for _ in range(40):                                      # the pool is bounded
+        L.give_back((L.Allocator(dev),))
+    assert len(L._alloc_pool[dev]) <= 16
+    L._alloc_pool.pop(dev, None)
+
+
+def test_device_guard_and_stream_helpers_fall_back_without_an_index():
+    """on_device / stream_ptr take the fast path only for an indexed CUDA device that is current; anything else goes
+    through torch's own objects (here: no GPU, so only the dispatch is checked)."""
+    from dogs_b200 import _lib as L
+    assert isinstance(L.on_device(torch.device("cuda")), torch.cuda.device)      # no index: torch's guard
+    assert isinstance(L.on_device("cuda:0"), torch.cuda.device)                   # a string: torch's guard
+    with L._NO_GUARD as g:
+        assert g is L._NO_GUARD
