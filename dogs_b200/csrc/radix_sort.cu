@@ -272,7 +272,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n_cap, int shift, 
   // every load of the chunk is in flight before the first count (ncu of the first version: 16 registers, one
   // load per thread at a time, 49 stall cycles per instruction on the scoreboard, 1.4 TB/s); a full chunk
   // comes as 16-byte loads, two per thread — the order of the keys does not matter to a histogram
-  if (base + SORT_CHUNK <= n) {
+  if (base + SORT_CHUNK <= n && (((uintptr_t)keys) & 15) == 0) {
     const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);
     uint4 v[SORT_ITEMS / 4];
 #pragma unroll
